@@ -1,0 +1,277 @@
+/*
+ * tal_b200.h — C ABI of the B200-native discrete-domain GP hot path.
+ *
+ * The reference (jonhue/transductive-active-learning) has no FFI layer: its L0
+ * is jax.numpy/XLA.  This header declares the entry points that take L0's
+ * place.  Each export cites the reference call site (path:line under the
+ * reference tree) whose arithmetic it replaces.  The Python binding a
+ * maintainer would add is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.
+ *  - Every pointer is a DEVICE pointer owned by the caller unless the
+ *    parameter name ends in `_host`.
+ *  - Every call only enqueues work on `stream` (a cudaStream_t passed as
+ *    void*) and returns without synchronising.  Return value: TAL_OK or a
+ *    TAL_ERR_* code; `tal_last_error_string()` describes the last failure
+ *    on the calling thread.
+ *  - Matrices are row-major.  A covariance shard is `cov[q][n_loc][ld]`
+ *    (GP-major, then local row, then column; `ld >= N` elements between
+ *    rows, `cov_stride_q` elements between GPs).  Local row r is global row
+ *    `row0 + r`.  On one GPU row0 = 0 and n_loc = N.
+ *  - `dtype` selects the storage/arithmetic type of covariance-sized data
+ *    (cov, kbuf, wbuf): TAL_F64 (the reference's only mode) or TAL_F32.
+ *    ld must be N rounded up to a multiple of 32 elements; the pad columns
+ *    hold zeros.  kbuf and wbuf are [q][ld] of the same dtype.
+ *    The O(qN) state vectors (mean, var, l, u, rho, F) are always double.
+ *  - Indices are int64 (`long long`), masks are one byte per point.
+ *  - q <= TAL_MAX_Q.
+ */
+#ifndef TAL_B200_H
+#define TAL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAL_ABI_VERSION 1
+#define TAL_MAX_Q 16
+
+/* status codes */
+#define TAL_OK 0
+#define TAL_ERR_CUDA 1        /* CUDA runtime / launch error */
+#define TAL_ERR_ARG 5         /* invalid argument */
+/* result.status of tal_masked_argmax — lib/model/marginal.py:336-342 */
+#define TAL_ARGMAX_OK 0
+#define TAL_ARGMAX_EMPTY_SAFE_SET 2 /* "Operating safe set is empty. Cannot make observations." */
+#define TAL_ARGMAX_ALL_NEG_INF 3    /* "Objective is negative infinity everywhere." */
+#define TAL_ARGMAX_ALL_NAN 4        /* "Objective is NaN everywhere." */
+
+/* dtype */
+#define TAL_F64 0
+#define TAL_F32 1
+
+/* stationary kernel kinds — lib/gp/kernels/stationary.py:23-55 */
+#define TAL_KERNEL_GAUSSIAN 0
+#define TAL_KERNEL_LAPLACE 1
+#define TAL_KERNEL_MATERN32 2
+#define TAL_KERNEL_MATERN52 3
+#define TAL_KERNEL_LINEAR 4 /* lib/gp/kernels/non_stationary.py:11-13 */
+
+/* row-reduce scoring rules — lib/algorithms/{vtl,ctl,mm_itl}.py, tru_var/__init__.py */
+#define TAL_RULE_VTL 0
+#define TAL_RULE_CTL 1
+#define TAL_RULE_MMITL 2
+#define TAL_RULE_TRUVAR 3
+
+/* result record written by tal_masked_argmax (32 bytes, device memory) */
+typedef struct tal_argmax_result {
+  long long idx;    /* lowest index among the exact ties at the maximum; -1 if none */
+  double val;       /* nanmax of the safety-masked objective */
+  long long n_ties; /* number of points attaining val exactly */
+  int status;       /* TAL_ARGMAX_* (derived from flags) */
+  int flags;        /* bit0: safe set non-empty; bit1: some F != -inf; bit2: some safe F not NaN */
+} tal_argmax_result;
+
+/* ---- library --------------------------------------------------------- */
+int tal_abi_version(void);
+const char* tal_last_error_string(void);
+/* number of kernels launched by this library in this process (bench.py's
+ * `gpu_launches`); reset with tal_reset_launch_count. */
+long long tal_launch_count(void);
+void tal_reset_launch_count(void);
+/* 1 if the library was built for sm_100a and the current device is CC 10.x */
+int tal_device_ok(void);
+
+/* ---- Gram construction ------------------------------------------------
+ * Replaces Kernel.cross_covariance / covariance (lib/gp/kernels/base.py:17-25)
+ * with the scalar kernels of stationary.py:23-55 / non_stationary.py:11-13.
+ * out[j][i] = k(X[i], Y[j]) for j in [j0, j0+n_rows): the reference returns
+ * [len(Y), len(X)] (vmap over X inside, over Y outside).  X is [n,d], Y is
+ * [m,d], both double, row-major.  `out` has `n_rows` rows of `ld` elements.
+ * If `mean_out`/`var_out` are non-null they are ignored (reserved).        */
+int tal_gram_stationary(int kind, const double* X, long long n, const double* Y, long long m,
+                        int d, double variance, double lengthscale, void* out, long long ld,
+                        long long j0, long long n_rows, int dtype, void* stream);
+
+/* ---- index lookup -------------------------------------------------------
+ * Replaces get_indices (lib/utils.py:53-56): out[k] = argmin_j ||X[j]-A[k]||_2
+ * with the first minimum winning.  X [n,d], A [m,d] double.                */
+int tal_nearest_index(const double* X, long long n, const double* A, long long m, int d,
+                      long long* out, void* stream);
+
+/* ---- posterior update, one observation (the BO loop's case) -----------
+ * Replaces MarginalModel.step (lib/model/marginal.py:350-368) →
+ * GaussianDistribution.posterior (lib/gp/gaussian_distribution.py:100-121) →
+ * _compute_posterior_covariance (:16-37) with m = 1, batched over q GPs.
+ *
+ * Phase 1, tal_extract_row: kbuf[i][:] = cov_i[idx, :] if this shard owns
+ *   global row idx, else zeros (so that a sum over shards is a broadcast);
+ *   also stashes mean_i[idx] into scal[i] (before it is overwritten).
+ *   `idx_dev` points to the observed index (device); if null, `idx_host` is used.
+ * Phase 2, tal_step_vectors (needs the complete kbuf): for each GP
+ *   s = k[idx] + rho[idx]^2, L = sqrt(s), w = (k / L) / L  (utils.py:22-23, 1x1),
+ *   mean' = mean + w (y - mean[idx]),  var' = var - k*w  (same arithmetic as
+ *   the matrix diagonal), l' = max(l, mean' - beta sqrt(var')),
+ *   u' = min(u, mean' + beta sqrt(var')) (marginal.py:160-164,366-367; NaN
+ *   propagating like jnp.maximum).  Writes wbuf[q][N].
+ *   y: if y_gather != 0, y_i = y_dev[i*y_stride + idx] else y_dev[i*y_stride].
+ * Phase 3, tal_rank1_update: cov_i[a][b] -= k_i[row0+a] * w_i[b] in place
+ *   over the shard (gaussian_distribution.py:36).  Pure HBM streaming:
+ *   2*q*n_loc*N*sizeof(T) algorithmic bytes.
+ *   variant: 0 = default, 1 = vectorised LDG/STG, 2 = bulk-async (TMA) pipeline. */
+int tal_extract_row(const void* cov, long long cov_stride_q, long long ld, long long row0,
+                    long long n_loc, long long N, int q, const long long* idx_dev,
+                    long long idx_host, const double* mean, void* kbuf, double* scal, int dtype,
+                    void* stream);
+int tal_step_vectors(const void* kbuf, void* wbuf, long long N, int q, const long long* idx_dev,
+                     long long idx_host, const double* y_dev, long long y_stride, int y_gather,
+                     const double* rho, const double* beta_host, const double* scal,
+                     double* mean, double* var, double* l, double* u, int dtype, void* stream);
+int tal_rank1_update(void* cov, long long cov_stride_q, long long ld, long long row0,
+                     long long n_loc, long long N, int q, const void* kbuf, const void* wbuf,
+                     int dtype, int variant, void* stream);
+
+/* ---- posterior update, m observations ---------------------------------
+ * Replaces GaussianDistribution.posterior for general m (prior_distr,
+ * lib/gp/prior.py:52-66; SafeOpt/GoOSE replay).  One GP per call.
+ * tal_gather_rows: B[j][:] = cov[obs_idx[j]-row0][:] (rows this shard owns;
+ *   others zero), B is [m][ldb] of the cov dtype converted to double.
+ * tal_small_posterior_weights: S = B[:, obs_idx] + diag(noise_std^2) (or
+ *   jitter^2 when noise_std is null: utils.py:44-50), L = chol(S),
+ *   W = S^-1 B (utils.py:22-23), mean' = mean + W^T (y - mean[obs_idx]),
+ *   var' = var - sum_j B[j]*W[j].  m <= 64.  NaN on Cholesky failure.
+ * tal_rankm_update: cov[a][b] -= sum_j B[j][row0+a] * W[j][b] in place.    */
+int tal_gather_rows(const void* cov, long long ld, long long row0, long long n_loc, long long N,
+                    const long long* obs_idx, long long m, double* B, long long ldb, int dtype,
+                    void* stream);
+int tal_small_posterior_weights(const double* B, long long ldb, long long N,
+                                const long long* obs_idx, int m, const double* noise_std,
+                                double jitter, const double* y, double* W, double* mean,
+                                double* var, void* stream);
+int tal_rankm_update(void* cov, long long ld, long long row0, long long n_loc, long long N,
+                     const double* B, const double* W, long long ldb, int m, int dtype,
+                     void* stream);
+
+/* ---- confidence-bound masks -------------------------------------------
+ * Replaces optimistic/pessimistic_safe_set, potential_expanders, max_l,
+ * potential_maximizers (lib/model/marginal.py:171-224).  l,u are [q][N].
+ * op_safe_in: the operating safe set when a subclass overrides it
+ * (unsafe.py:9-13, safe_opt/model.py:34-37); null = pessimistic.
+ * Any output pointer may be null.  max_l_out: one double.                 */
+int tal_bounds_masks(const double* l, const double* u, int q, int first_constraint, long long N,
+                     const unsigned char* op_safe_in, unsigned char* pess, unsigned char* opt,
+                     unsigned char* pm, unsigned char* pe, double* max_l_out, void* stream);
+/* ordered stream compaction: idx_out = indices where mask != 0 (ascending),
+ * *count_out = how many.  Replaces domain[mask] / set_to_idx (utils.py:74-75). */
+int tal_mask_to_indices(const unsigned char* mask, long long N, long long* idx_out,
+                        long long* count_out, void* stream);
+/* scalar-wise subset test of lib/utils.py:65-71 (jnp.isin on flattened
+ * coordinates) for X = domain[x_mask], A = domain[roi_idx]: sid[N][d] maps
+ * every coordinate to the id of its distinct scalar value; present is an
+ * [n_sid] byte scratch.  *out = 1 iff every scalar of X occurs in A;
+ * empty-set rules of :66-69 included.                                      */
+int tal_scalar_subset(const int* sid, int d, long long N, long long n_sid,
+                      const unsigned char* x_mask, const long long* roi_idx,
+                      const long long* roi_count_dev, long long roi_count_host,
+                      unsigned char* present, int* out, void* stream);
+
+/* ---- scoring ------------------------------------------------------------
+ * tal_score_itl_undirected: F[x] = sum_i log(1 + var_i[x]/rho_i[x]^2)
+ *   (lib/algorithms/itl.py:28-30).
+ *
+ * Row-reduce family (one GP per call).  The reference gathers cov[a, x] for
+ * a in the ROI through nested vmaps (vtl.py:21-41, marginal.py:129-158,
+ * tru_var/__init__.py:31-48); here the m ROI rows are streamed once and
+ * reduced per column:  c[x] = sum_{a in roi} elem(cov[a][x]) with
+ *   VTL, CTL:  elem = w_a v^2              (w_a = 1, resp. 1/var[a])
+ *   MM-ITL:    elem = -0.5 log(1 - w_a v^2 dinv[x]),  w_a = 1/var[a]
+ *   TruVar:    elem = max(p0 (w_a - v^2 dinv[x]), p1), w_a = var[a], p0 = beta, p1 = eta^2
+ * with dinv[x] = 1/(var[x] + rho[x]^2).
+ * tal_colsum_rows reads ROI rows a (coalesced; rows outside this shard are
+ *   skipped); `part` is an [n_split][N] scratch, c_out is [N].
+ * tal_colsum_cols computes the same sums for the shard's own candidates
+ *   x = row0 + r through the symmetric entries cov[r][a] (no communication;
+ *   used when the covariance is row-sharded); c_out and dinv are [n_loc].
+ * tal_roi_trace: tr = sum_{a in roi} var[a].  tal_roi_weights: w_a.
+ * tal_pred_var_inv: dinv.
+ * tal_score_rows_finish: F[x] (+)= epilogue over n candidates
+ *   VTL: -(tr - c/(var+rho^2)); CTL: c/(var+rho^2); MM-ITL: c; TruVar: -c.   */
+int tal_score_itl_undirected(const double* var, const double* rho, int q, long long N, double* F,
+                             void* stream);
+int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                    long long N, const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* part, int n_split,
+                    double* c_out, int dtype, void* stream);
+int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
+                    const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* c_out, int dtype,
+                    void* stream);
+int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,
+                  void* stream);
+int tal_roi_weights(const double* var, const long long* roi_idx, long long m, int reciprocal,
+                    double* out, void* stream);
+int tal_pred_var_inv(const double* var, const double* rho, long long N, double* out,
+                     void* stream);
+int tal_score_rows_finish(int rule, const double* c, const double* var, const double* rho,
+                          const double* tr, long long n, int accumulate, double* F,
+                          void* stream);
+
+/* ---- directed ITL conditioning (fp64, DMMA tensor path) ----------------
+ * Replaces compute_posterior_covariance(cov_i, roi_idx, None) + diag
+ * (lib/algorithms/itl.py:41-48; gaussian_distribution.py:16-37;
+ * utils.py:10-24,44-50) by: S = cov[A,A] + jitter^2 I, L = chol(S) (NaN on
+ * failure, like jnp.linalg.cholesky), V = L^-1 cov[A,:] (forward solve only),
+ * post_var[x] = var[x] - sum_j V[j][x]^2.
+ * m_pad = m rounded up to 128; column counts are multiples of 64.
+ * tal_gather_roi: B[j][x] = cov[roi[j]][x] (double, [m_pad][ldb], pad rows and
+ *   columns zero) and S = blockdiag(cov[A,A] + jitter^2 I, I) ([m_pad][lds]).
+ * tal_potrf_lower: in-place blocked Cholesky of S (lower).  work: scratch of
+ *   tal_potrf_work_bytes(m_pad); it receives the inverses of the diagonal
+ *   blocks, which tal_trsm_lower consumes.
+ * tal_trsm_lower: B <- L^-1 B, B is [m_pad][n_cols] with row stride ldb.
+ * tal_colsumsq_dense: out[x] = sum_j V[j][x]^2 (part: [n_split][n_cols]).
+ * tal_score_itl_directed: F[x] (+)= 0.5*max(log((var+rho^2)/(var-cs+rho^2)),0)
+ *   (itl.py:50-58) with cs the column sums of squares above.               */
+int tal_gather_roi(const void* cov, long long ld, long long N, const long long* roi_idx,
+                   long long m, long long m_pad, double jitter, double* S, long long lds,
+                   double* B, long long ldb, int dtype, void* stream);
+long long tal_potrf_work_bytes(long long m_pad);
+int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void* stream);
+int tal_trsm_lower(const double* L, long long lds, long long m_pad, const void* work, double* B,
+                   long long ldb, long long n_cols, void* stream);
+int tal_colsumsq_dense(const double* V, long long ldv, long long m, long long n_cols,
+                       double* part, int n_split, double* out, void* stream);
+int tal_score_itl_directed(const double* var, const double* cs, const double* rho,
+                           long long n, int accumulate, double* F, void* stream);
+
+/* ---- masked arg-max -----------------------------------------------------
+ * Replaces DiscreteGreedyAlgorithm._step's sample-region masking
+ * (lib/algorithms/__init__.py:80) + MarginalModel.objective_argmax
+ * (lib/model/marginal.py:330-348) up to the PRNG draw.  F_io [N] is
+ * overwritten with the sample-region-masked objective (the "F" of the result
+ * dict).  safe: operating safe set; if null it is computed on the fly as the
+ * pessimistic safe set all_{i>=fc} l_i[x] >= 0 (fused safe-set mask).
+ * sample: sample-region mask or null (all true).  idx_offset is added to the
+ * reported index (shard's first candidate).  scratch: tal_argmax_scratch_bytes().
+ * Tie policy: lowest index among exact ties (the reference draws uniformly
+ * with jax.random.choice); n_ties reports the size of the tie set.         */
+long long tal_argmax_scratch_bytes(void);
+int tal_masked_argmax(double* F_io, const unsigned char* safe, const double* l, int q,
+                      int first_constraint, long long l_stride, const unsigned char* sample,
+                      long long N, long long idx_offset, void* scratch, tal_argmax_result* out,
+                      void* stream);
+/* lexicographic reduce of G per-shard results (max val, then min idx; statuses
+ * combined) — the all-reduce of the per-shard arg-max after an all-gather. */
+int tal_argmax_combine(const tal_argmax_result* parts, int G, tal_argmax_result* out,
+                       void* stream);
+
+/* ---- fp64 peak probes (roofline denominators of the tensor path) --------
+ * kind 0: DMMA.8x8x4, kind 1: DFMA; `blocks` CTAs x 256 threads x iters x 16
+ * independent ops.  flops = blocks*iters*16*(kind==0 ? 8*512 : 256*2).     */
+int tal_probe_fp64(int kind, int blocks, int iters, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAL_B200_H */

@@ -1,0 +1,493 @@
+// Target-set conditioning for directed ITL, in fp64 on the DMMA tensor path.
+//
+// Reference path: ITL._directed (lib/algorithms/itl.py:33-60) calls
+// compute_posterior_covariance(cov_i, roi_idx, None)
+// (lib/gp/gaussian_distribution.py:16-55): Sigma_AA + jitter^2 I
+// (lib/utils.py:44-50), solve_linear_system = cholesky + two solves
+// (lib/utils.py:10-24), then an N x N x m GEMM of which only the diagonal is
+// used (itl.py:48).  Here: gather, blocked Cholesky, forward TRSM only, and a
+// column sum of squares:  post_var[x] = var[x] - || L^-1 cov[A, x] ||^2.
+//
+// All dense contractions (SYRK trailing update, panel solve, TRSM) run on
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — the only fp64 tensor shape on
+// sm_100a; tcgen05 has no f64 kind) with cp.async multi-stage staging.
+// m and the column count are padded by the caller to multiples of the tiles.
+#include "common.cuh"
+
+namespace tal {
+
+constexpr int NB = 128;  // Cholesky / TRSM block size (rows of a block row)
+
+// --------------------------------------------------------------------------
+// gather
+// --------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_roi_B_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restrict__ roi_idx,
+                    i64 m, double* __restrict__ B, i64 ldb) {
+  // grid.y over padded rows; pad rows / pad columns are zero
+  const i64 j = blockIdx.y;
+  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ldb) return;
+  double v = 0.0;
+  if (j < m && col < N) v = (double)cov[roi_idx[j] * ld + col];
+  B[j * ldb + col] = v;
+}
+
+__global__ void __launch_bounds__(256)
+gather_roi_S_kernel(const double* __restrict__ B, i64 ldb, const i64* __restrict__ roi_idx, i64 m,
+                    i64 m_pad, double jitter, double* __restrict__ S, i64 lds) {
+  const i64 j = blockIdx.y;
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m_pad) return;
+  double v;
+  if (j < m && k < m) {
+    v = B[j * ldb + roi_idx[k]];
+    if (j == k) v = v + jitter * jitter;  // identity(k) * square(default) (utils.py:48-50)
+  } else {
+    v = (j == k) ? 1.0 : 0.0;  // pad: blockdiag(S, I)
+  }
+  S[j * lds + k] = v;
+}
+
+// --------------------------------------------------------------------------
+// DMMA GEMM core:  acc[BM x BN] += A[BM x K] * B[K x BN]
+//   A row-major (k contiguous).  B either [k][n] (NN) or [n][k] (NT).
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+struct GemmCfg {
+  static constexpr int BM = BM_, BN = BN_, BK = 16, WM = WM_, WN = WN_, STAGES = STAGES_;
+  static constexpr int THREADS = WM * WN * 32;
+  static constexpr int WTM = BM / WM, WTN = BN / WN;  // warp tile
+  static constexpr int MF = WTM / 8, NF = WTN / 8;    // 8x8 fragments per warp tile
+  static constexpr int SA = BK + 4;                   // A smem row stride (doubles), == 4 mod 16
+  static constexpr int SB_NN = BN + 4;                // B [k][n] row stride, == 4 mod 16
+  static constexpr int SB_NT = BK + 4;                // B [n][k] row stride
+  static constexpr int A_ELEMS = BM * SA;
+  static constexpr int B_ELEMS = (BK * SB_NN > BN * SB_NT) ? BK * SB_NN : BN * SB_NT;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_ELEMS * sizeof(double);
+  static_assert(BN % 16 == 0 && BM % (WM * 8) == 0 && BN % (WN * 8) == 0, "tile shape");
+};
+
+template <class C, bool NT>
+__device__ __forceinline__ void gemm_load_stage(double* st, const double* __restrict__ A, i64 lda,
+                                                const double* __restrict__ Bm, i64 ldb, int k0) {
+  // A tile: BM rows x 16 doubles = BM * 8 chunks of 16 B
+  double* As = st;
+  double* Bs = st + C::A_ELEMS;
+  for (int c = threadIdx.x; c < C::BM * 8; c += C::THREADS) {
+    const int r = c >> 3, ch = c & 7;
+    cp_async16(As + r * C::SA + ch * 2, A + (i64)r * lda + k0 + ch * 2);
+  }
+  if constexpr (NT) {
+    for (int c = threadIdx.x; c < C::BN * 8; c += C::THREADS) {
+      const int r = c >> 3, ch = c & 7;
+      cp_async16(Bs + r * C::SB_NT + ch * 2, Bm + (i64)r * ldb + k0 + ch * 2);
+    }
+  } else {
+    constexpr int CPR = C::BN / 2;  // chunks per row
+    for (int c = threadIdx.x; c < C::BK * CPR; c += C::THREADS) {
+      const int r = c / CPR, ch = c % CPR;
+      cp_async16(Bs + r * C::SB_NN + ch * 2, Bm + (i64)(k0 + r) * ldb + ch * 2);
+    }
+  }
+}
+
+// acc layout: acc[mf][nf][2] : row = wm*WTM + mf*8 + (lane>>2), col = wn*WTN + nf*8 + (lane&3)*2 + e
+template <class C, bool NT>
+__device__ __forceinline__ void gemm_accumulate(double* smem, const double* __restrict__ A, i64 lda,
+                                                const double* __restrict__ Bm, i64 ldb, int K,
+                                                double (&acc)[C::MF][C::NF][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / C::WN, wn = warp % C::WN;
+  const int g = lane >> 2, t = lane & 3;
+  const int nk = K / C::BK;
+  if (nk == 0) return;
+  // prologue
+#pragma unroll
+  for (int s = 0; s < C::STAGES - 1; ++s) {
+    if (s < nk) gemm_load_stage<C, NT>(smem + s * C::STAGE_ELEMS, A, lda, Bm, ldb, s * C::BK);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<C::STAGES - 2>();
+    __syncthreads();
+    // prefetch tile kt + STAGES - 1 into the slot freed at iteration kt - 1
+    const int nxt = kt + C::STAGES - 1;
+    if (nxt < nk)
+      gemm_load_stage<C, NT>(smem + (nxt % C::STAGES) * C::STAGE_ELEMS, A, lda, Bm, ldb, nxt * C::BK);
+    cp_async_commit();
+    const double* As = smem + (kt % C::STAGES) * C::STAGE_ELEMS;
+    const double* Bs = As + C::A_ELEMS;
+#pragma unroll
+    for (int ks = 0; ks < C::BK / 4; ++ks) {
+      double a[C::MF], b[C::NF];
+#pragma unroll
+      for (int mf = 0; mf < C::MF; ++mf)
+        a[mf] = As[(wm * C::WTM + mf * 8 + g) * C::SA + ks * 4 + t];
+#pragma unroll
+      for (int nf = 0; nf < C::NF; ++nf) {
+        if constexpr (NT) b[nf] = Bs[(wn * C::WTN + nf * 8 + g) * C::SB_NT + ks * 4 + t];
+        else b[nf] = Bs[(ks * 4 + t) * C::SB_NN + wn * C::WTN + nf * 8 + g];
+      }
+#pragma unroll
+      for (int mf = 0; mf < C::MF; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < C::NF; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], a[mf], b[nf]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+template <class C>
+__device__ __forceinline__ void acc_zero(double (&acc)[C::MF][C::NF][2]) {
+#pragma unroll
+  for (int mf = 0; mf < C::MF; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < C::NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+}
+
+// MODE 0: D = acc ; MODE 1: D = D - acc
+template <class C, int MODE>
+__device__ __forceinline__ void acc_store(double* __restrict__ D, i64 ldd,
+                                          const double (&acc)[C::MF][C::NF][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp / C::WN, wn = warp % C::WN;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mf = 0; mf < C::MF; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < C::NF; ++nf) {
+      double2* p = reinterpret_cast<double2*>(D + (i64)(wm * C::WTM + mf * 8 + g) * ldd +
+                                              wn * C::WTN + nf * 8 + t * 2);
+      double2 v;
+      if constexpr (MODE == 1) {
+        v = *p;
+        v.x -= acc[mf][nf][0];
+        v.y -= acc[mf][nf][1];
+      } else {
+        v.x = acc[mf][nf][0];
+        v.y = acc[mf][nf][1];
+      }
+      *p = v;
+    }
+}
+
+typedef GemmCfg<128, 64, 4, 2, 4> TrsmCfg;  // 256 threads, warp tile 32 x 32
+
+// --------------------------------------------------------------------------
+// TRSM:  B <- L^-1 B.  One CTA per strip of BN columns; block row i:
+//   T_i = B_i - sum_{j<i} L_ij X_j          (DMMA, K = i * NB)
+//   X_i = inv(L_ii) T_i                     (DMMA, K = NB)
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(TrsmCfg::THREADS)
+trsm_lower_kernel(const double* __restrict__ L, i64 lds, int m, const double* __restrict__ Linv,
+                  double* __restrict__ B, i64 ldb) {
+  typedef TrsmCfg C;
+  extern __shared__ __align__(16) double smem[];
+  double* Bs = B + (i64)blockIdx.x * C::BN;
+  double acc[C::MF][C::NF][2];
+  const int nblk = m / NB;
+  for (int i = 0; i < nblk; ++i) {
+    double* Bi = Bs + (i64)i * NB * ldb;
+    if (i > 0) {
+      acc_zero<C>(acc);
+      gemm_accumulate<C, false>(smem, L + (i64)i * NB * lds, lds, Bs, ldb, i * NB, acc);
+      acc_store<C, 1>(Bi, ldb, acc);
+      __threadfence_block();
+      __syncthreads();
+    }
+    acc_zero<C>(acc);
+    gemm_accumulate<C, false>(smem, Linv + (i64)i * NB * NB, NB, Bi, ldb, NB, acc);
+    acc_store<C, 0>(Bi, ldb, acc);
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------
+// Cholesky, right-looking, block size NB.
+// --------------------------------------------------------------------------
+// (1) factor the diagonal block in shared memory, write L_jj and inv(L_jj).
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ Linv_all) {
+  extern __shared__ __align__(16) double sm[];  // [NB][NB+1]
+  constexpr int P = NB + 1;
+  double* D = S + (i64)j * NB * lds + (i64)j * NB;
+  double* Linv = Linv_all + (i64)j * NB * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    sm[r * P + c] = (c <= r) ? D[(i64)r * lds + c] : 0.0;
+  }
+  __syncthreads();
+  for (int c = 0; c < NB; ++c) {
+    if (threadIdx.x == 0) sm[c * P + c] = sqrt(sm[c * P + c]);  // NaN if not positive definite
+    __syncthreads();
+    const double d = sm[c * P + c];
+    for (int r = c + 1 + threadIdx.x; r < NB; r += blockDim.x) sm[r * P + c] /= d;
+    __syncthreads();
+    // trailing update of the lower triangle: rows r > c, cols c < k <= r
+    const int n = NB - c - 1;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+      const int r = c + 1 + e / n, k = c + 1 + e % n;
+      if (k <= r) sm[r * P + k] -= sm[r * P + c] * sm[k * P + c];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    if (c <= r) D[(i64)r * lds + c] = sm[r * P + c];
+  }
+  // inverse by forward substitution, one column per thread (columns >= NB idle)
+  const int c = threadIdx.x;
+  if (c < NB) {
+    for (int r = 0; r < NB; ++r) {
+      double x;
+      if (r < c) {
+        x = 0.0;
+      } else {
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int k = c; k < r; ++k) s -= sm[r * P + k] * Linv[k * NB + c];
+        x = s / sm[r * P + r];
+      }
+      Linv[r * NB + c] = x;
+    }
+  }
+}
+
+typedef GemmCfg<128, 128, 4, 2, 3> PanelCfg;  // one CTA owns a whole NB x NB block
+typedef GemmCfg<128, 64, 4, 2, 3> SyrkCfg;
+
+// (2) panel:  L_ij = S_ij inv(L_jj)^T  for block rows i > j, in place.
+//     One CTA per block row reads all of S_ij before it writes it back.
+__global__ void __launch_bounds__(PanelCfg::THREADS)
+potrf_panel_kernel(double* __restrict__ S, i64 lds, int j, const double* __restrict__ Linv_all) {
+  typedef PanelCfg C;
+  extern __shared__ __align__(16) double smem[];
+  const int i = j + 1 + blockIdx.x;
+  const double* Linv = Linv_all + (i64)j * NB * NB;
+  double* Sij = S + (i64)i * NB * lds + (i64)j * NB;
+  double acc[C::MF][C::NF][2];
+  acc_zero<C>(acc);
+  // C[r][n] = sum_k S_ij[r][k] * Linv[n][k]
+  gemm_accumulate<C, true>(smem, Sij, lds, Linv, NB, NB, acc);
+  acc_store<C, 0>(Sij, lds, acc);
+}
+
+// (3) trailing update:  S_ik -= L_ij L_kj^T  for j < k <= i.
+//     grid.x enumerates the (i, k) block pairs of the trailing lower triangle,
+//     grid.y the BN-wide halves of a block.
+__global__ void __launch_bounds__(SyrkCfg::THREADS)
+potrf_syrk_kernel(double* __restrict__ S, i64 lds, int j) {
+  typedef SyrkCfg C;
+  extern __shared__ __align__(16) double smem[];
+  // decode pair index p -> (a, b) with 0 <= b <= a: a = floor((sqrt(8p+1)-1)/2)
+  const int p = blockIdx.x;
+  int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= p) ++a;
+  while (a * (a + 1) / 2 > p) --a;
+  const int b = p - a * (a + 1) / 2;
+  const int i = j + 1 + a, k = j + 1 + b;
+  const int n0 = blockIdx.y * C::BN;
+  const double* Lij = S + (i64)i * NB * lds + (i64)j * NB;
+  const double* Lkj = S + ((i64)k * NB + n0) * lds + (i64)j * NB;
+  double* Sik = S + (i64)i * NB * lds + (i64)k * NB + n0;
+  double acc[C::MF][C::NF][2];
+  acc_zero<C>(acc);
+  gemm_accumulate<C, true>(smem, Lij, lds, Lkj, lds, NB, acc);
+  acc_store<C, 1>(Sik, lds, acc);
+}
+
+// --------------------------------------------------------------------------
+// out[x] = sum_j V[j][x]^2   (dense column sums of squares; HBM-bound read)
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsumsq_dense_kernel(const double* __restrict__ V, i64 ldv, i64 m, i64 n_cols,
+                      double* __restrict__ part) {
+  const i64 col = ((i64)blockIdx.x * 256 + threadIdx.x) * 2;
+  if (col >= n_cols) return;
+  const i64 per = (m + gridDim.y - 1) / gridDim.y;
+  const i64 j0 = (i64)blockIdx.y * per, j1 = min(m, j0 + per);
+  double a0 = 0.0, a1 = 0.0;
+  for (i64 j = j0; j < j1; j += 4) {
+    double2 c[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (j + t < j1) c[t] = ld_stream(reinterpret_cast<const double2*>(V + (j + t) * ldv + col));
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (j + t < j1) { a0 += c[t].x * c[t].x; a1 += c[t].y * c[t].y; }
+  }
+  part[(i64)blockIdx.y * n_cols + col] = a0;
+  if (col + 1 < n_cols) part[(i64)blockIdx.y * n_cols + col + 1] = a1;
+}
+
+__global__ void __launch_bounds__(256)
+postvar_kernel(const double* __restrict__ part, int n_split, i64 n_cols, double* __restrict__ out) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_cols) return;
+  double acc = 0.0;
+  for (int s = 0; s < n_split; ++s) acc += part[(i64)s * n_cols + x];
+  out[x] = acc;
+}
+
+template <class C, class K>
+static int set_smem(K kern, bool& done) {
+  if (!done) {
+    TAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)C::SMEM_BYTES));
+    done = true;
+  }
+  return TAL_OK;
+}
+
+}  // namespace tal
+
+using namespace tal;
+
+extern "C" {
+
+int tal_gather_roi(const void* cov, long long ld, long long N, const long long* roi_idx,
+                   long long m, long long m_pad, double jitter, double* S, long long lds,
+                   double* B, long long ldb, int dtype, void* stream) {
+  TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
+  TAL_ARG(lds >= m_pad && ldb >= N && m_pad <= 65535);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  cudaStream_t st = as_stream(stream);
+  dim3 gb((unsigned)((ldb + 255) / 256), (unsigned)m_pad);
+  if (dtype == TAL_F64)
+    gather_roi_B_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, N, roi_idx, m, B, ldb);
+  else
+    gather_roi_B_kernel<float><<<gb, 256, 0, st>>>((const float*)cov, ld, N, roi_idx, m, B, ldb);
+  TAL_LAUNCH_CHECK("tal_gather_roi/B");
+  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
+  TAL_LAUNCH_CHECK("tal_gather_roi/S");
+  return TAL_OK;
+}
+
+long long tal_potrf_work_bytes(long long m_pad) {
+  return (m_pad / NB) * (long long)NB * NB * (long long)sizeof(double);
+}
+
+int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void* stream) {
+  TAL_ARG(S && work && m_pad >= NB && m_pad % NB == 0 && lds >= m_pad && lds % 2 == 0);
+  cudaStream_t st = as_stream(stream);
+  static bool a0 = false, a1 = false, a2 = false;
+  const int diag_smem = NB * (NB + 1) * (int)sizeof(double);
+  if (!a0) {
+    TAL_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  diag_smem));
+    a0 = true;
+  }
+  if (set_smem<PanelCfg>(potrf_panel_kernel, a1) != TAL_OK) return TAL_ERR_CUDA;
+  if (set_smem<SyrkCfg>(potrf_syrk_kernel, a2) != TAL_OK) return TAL_ERR_CUDA;
+  const int nblk = (int)(m_pad / NB);
+  double* Linv = (double*)work;
+  for (int j = 0; j < nblk; ++j) {
+    potrf_diag_kernel<<<1, 256, diag_smem, st>>>(S, lds, j, Linv);
+    TAL_LAUNCH_CHECK("tal_potrf_lower/diag");
+    const int rem = nblk - j - 1;
+    if (rem > 0) {
+      potrf_panel_kernel<<<rem, PanelCfg::THREADS, PanelCfg::SMEM_BYTES, st>>>(S, lds, j, Linv);
+      TAL_LAUNCH_CHECK("tal_potrf_lower/panel");
+      dim3 g((unsigned)(rem * (rem + 1) / 2), NB / SyrkCfg::BN);
+      potrf_syrk_kernel<<<g, SyrkCfg::THREADS, SyrkCfg::SMEM_BYTES, st>>>(S, lds, j);
+      TAL_LAUNCH_CHECK("tal_potrf_lower/syrk");
+    }
+  }
+  return TAL_OK;
+}
+
+int tal_trsm_lower(const double* L, long long lds, long long m_pad, const void* work, double* B,
+                   long long ldb, long long n_cols, void* stream) {
+  TAL_ARG(L && work && B && m_pad >= NB && m_pad % NB == 0 && lds >= m_pad && lds % 2 == 0);
+  TAL_ARG(n_cols >= 1 && n_cols % TrsmCfg::BN == 0 && ldb >= n_cols && ldb % 2 == 0);
+  static bool a = false;
+  if (set_smem<TrsmCfg>(trsm_lower_kernel, a) != TAL_OK) return TAL_ERR_CUDA;
+  trsm_lower_kernel<<<(unsigned)(n_cols / TrsmCfg::BN), TrsmCfg::THREADS, TrsmCfg::SMEM_BYTES,
+                      as_stream(stream)>>>(L, lds, (int)m_pad, (const double*)work, B, ldb);
+  TAL_LAUNCH_CHECK("tal_trsm_lower");
+  return TAL_OK;
+}
+
+int tal_colsumsq_dense(const double* V, long long ldv, long long m, long long n_cols,
+                       double* part, int n_split, double* out, void* stream) {
+  TAL_ARG(V && part && out && m >= 1 && n_cols >= 1 && ldv >= n_cols && ldv % 2 == 0);
+  TAL_ARG(n_split >= 1 && n_split <= 65535);
+  cudaStream_t st = as_stream(stream);
+  dim3 grid((unsigned)((n_cols + 511) / 512), (unsigned)n_split);
+  colsumsq_dense_kernel<<<grid, 256, 0, st>>>(V, ldv, m, n_cols, n_split == 1 ? out : part);
+  TAL_LAUNCH_CHECK("tal_colsumsq_dense");
+  if (n_split > 1) {
+    postvar_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(part, n_split, n_cols, out);
+    TAL_LAUNCH_CHECK("tal_colsumsq_dense/sum");
+  }
+  return TAL_OK;
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------
+// Peak probes (roofline denominators for the fp64 tensor path)
+// --------------------------------------------------------------------------
+namespace tal {
+__global__ void __launch_bounds__(256) probe_dmma_kernel(int iters, double* __restrict__ out) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) probe_dfma_kernel(int iters, double* __restrict__ out) {
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = threadIdx.x * 1e-3 + i;
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i];
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace tal
+
+extern "C" {
+/* kind 0: DMMA.8x8x4 (2*256 flop per warp instruction), kind 1: DFMA.  Launches
+ * `blocks` CTAs of 256 threads running `iters` x 16 independent ops per thread;
+ * flops = blocks * iters * 16 * (kind == 0 ? 8 * 512 : 256 * 2).              */
+int tal_probe_fp64(int kind, int blocks, int iters, double* out, void* stream) {
+  TAL_ARG(out && blocks >= 1 && iters >= 1);
+  if (kind == 0) tal::probe_dmma_kernel<<<blocks, 256, 0, tal::as_stream(stream)>>>(iters, out);
+  else tal::probe_dfma_kernel<<<blocks, 256, 0, tal::as_stream(stream)>>>(iters, out);
+  TAL_LAUNCH_CHECK("tal_probe_fp64");
+  return TAL_OK;
+}
+}

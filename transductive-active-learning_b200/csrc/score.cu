@@ -1,0 +1,340 @@
+// Per-candidate acquisition scores.
+//
+// Reference path: ITL._undirected (lib/algorithms/itl.py:28-30), VTL.F
+// (lib/algorithms/vtl.py:16-41) and the CTL / MM-ITL reductions over
+// MarginalModel.sqd_correlation (lib/model/marginal.py:129-158,
+// lib/algorithms/ctl.py:14-17, mm_itl.py:14-17).  The reference gathers
+// cov[a, x] for a in the ROI through nested vmaps; here the ROI rows are
+// streamed once (m*N*sizeof(T) bytes) and reduced per column.
+#include "common.cuh"
+
+namespace tal {
+
+__global__ void __launch_bounds__(256)
+itl_undirected_kernel(const double* __restrict__ var, const double* __restrict__ rho, int q, i64 N,
+                      double* __restrict__ F) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= N) return;
+  double acc = 0.0;
+  for (int i = 0; i < q; ++i) {
+    const double r = rho[(i64)i * N + x];
+    acc += log(1.0 + var[(i64)i * N + x] / (r * r));  // itl.py:29-30 (no 1/2)
+  }
+  F[x] = acc;
+}
+
+// Element functor of the row reduce: what each cov[a][x] contributes.
+//   VTL / CTL:  w_a * v^2
+//   MM-ITL:    -0.5 * log(1 - w_a * v^2 * dinv[x])      (mm_itl.py:15-16)
+//   TruVar:     max(beta * (var_a - v^2 * dinv[x]), eta^2) (tru_var/__init__.py:31-45)
+template <int RULE>
+__device__ __forceinline__ double elem(double v, double wa, double dinv, double p0, double p1) {
+  if constexpr (RULE == TAL_RULE_VTL || RULE == TAL_RULE_CTL) {
+    return wa * (v * v);
+  } else if constexpr (RULE == TAL_RULE_MMITL) {
+    return -0.5 * log(1.0 - (v * v) * wa * dinv);
+  } else {
+    return fmax(p0 * (wa - (v * v) * dinv), p1);
+  }
+}
+
+// Column sums over ROI rows.  grid = (column tiles, row splits).  Each thread
+// owns one 16-byte vector of columns; ROI rows [j0, j1) of its split are read
+// UNROLL at a time so that UNROLL independent 16-byte loads are in flight.
+template <typename T, int RULE, int UNROLL>
+__global__ void __launch_bounds__(256)
+colsum_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N,
+                   const i64* __restrict__ roi_idx, i64 m, const double* __restrict__ row_weight,
+                   const double* __restrict__ dinv, double p0, double p1,
+                   double* __restrict__ part) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
+  const i64 col = ((i64)blockIdx.x * 256 + threadIdx.x) * VN;
+  const i64 per = (m + gridDim.y - 1) / gridDim.y;
+  const i64 j0 = (i64)blockIdx.y * per;
+  const i64 j1 = min(m, j0 + per);
+  if (col >= ld) return;
+  double acc[VN];
+  double di[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    acc[e] = 0.0;
+    di[e] = (dinv && col + e < N) ? dinv[col + e] : 0.0;
+  }
+  for (i64 j = j0; j < j1; j += UNROLL) {
+    V c[UNROLL];
+    double wa[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      ok[t] = false;
+      if (j + t < j1) {
+        const i64 r = roi_idx[j + t] - row0;
+        if (r >= 0 && r < n_loc) {
+          ok[t] = true;
+          c[t] = ld_stream(reinterpret_cast<const V*>(cov + r * ld + col));
+          wa[t] = row_weight ? row_weight[j + t] : 1.0;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      if (ok[t]) {
+        if constexpr (VN == 2) {
+          acc[0] += elem<RULE>((double)c[t].x, wa[t], di[0], p0, p1);
+          acc[1] += elem<RULE>((double)c[t].y, wa[t], di[1], p0, p1);
+        } else {
+          acc[0] += elem<RULE>((double)c[t].x, wa[t], di[0], p0, p1);
+          acc[1] += elem<RULE>((double)c[t].y, wa[t], di[1], p0, p1);
+          acc[2] += elem<RULE>((double)c[t].z, wa[t], di[2], p0, p1);
+          acc[3] += elem<RULE>((double)c[t].w, wa[t], di[3], p0, p1);
+        }
+      }
+    }
+  }
+  double* o = part + (i64)blockIdx.y * N;
+#pragma unroll
+  for (int e = 0; e < VN; ++e)
+    if (col + e < N) o[col + e] = acc[e];
+}
+
+__global__ void __launch_bounds__(256)
+sum_parts_kernel(const double* __restrict__ part, int n_split, i64 N, double* __restrict__ out) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= N) return;
+  double acc = 0.0;
+  for (int s = 0; s < n_split; ++s) acc += part[(i64)s * N + x];  // fixed order: deterministic
+  out[x] = acc;
+}
+
+// Same sums for the shard's own candidates through the symmetric entries
+// cov[r][a]: one warp per local row, lanes stride over the ROI.
+template <typename T, int RULE>
+__global__ void __launch_bounds__(256)
+colsum_cols_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, const i64* __restrict__ roi_idx,
+                   i64 m, const double* __restrict__ row_weight, const double* __restrict__ dinv,
+                   double p0, double p1, double* __restrict__ out) {
+  const i64 r = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_loc) return;
+  const T* row = cov + r * ld;
+  const double di = dinv ? dinv[r] : 0.0;
+  double acc = 0.0;
+  for (i64 j = lane; j < m; j += 32) {
+    const double v = (double)row[roi_idx[j]];
+    acc += elem<RULE>(v, row_weight ? row_weight[j] : 1.0, di, p0, p1);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
+}
+
+// tr_A = sum_{a in roi} var[a]  (one block, deterministic)
+__global__ void __launch_bounds__(256)
+roi_trace_kernel(const double* __restrict__ var, const i64* __restrict__ roi_idx, i64 m,
+                 double* __restrict__ out) {
+  __shared__ double sh[33];
+  double acc = 0.0;
+  for (i64 j = threadIdx.x; j < m; j += blockDim.x) acc += var[roi_idx[j]];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+// w_a for the CTL / MM-ITL (1/var[a]) and TruVar (var[a]) rules
+__global__ void __launch_bounds__(256)
+roi_weights_kernel(const double* __restrict__ var, const i64* __restrict__ roi_idx, i64 m,
+                   int reciprocal, double* __restrict__ out) {
+  const i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const double v = var[roi_idx[j]];
+  out[j] = reciprocal ? 1.0 / v : v;
+}
+
+// dinv[x] = 1 / (var[x] + rho[x]^2)
+__global__ void __launch_bounds__(256)
+pred_var_inv_kernel(const double* __restrict__ var, const double* __restrict__ rho, i64 N,
+                    double* __restrict__ out) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= N) return;
+  const double r = rho[x];
+  out[x] = 1.0 / (var[x] + r * r);
+}
+
+__global__ void __launch_bounds__(256)
+rows_finish_kernel(int rule, const double* __restrict__ c, const double* __restrict__ var,
+                   const double* __restrict__ rho, const double* __restrict__ tr, i64 n,
+                   int accumulate, double* __restrict__ F) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  double f;
+  if (rule == TAL_RULE_VTL) {
+    const double r = rho[x];
+    f = -(*tr - c[x] / (var[x] + r * r));  // vtl.py:29-41, summed over the ROI
+  } else if (rule == TAL_RULE_CTL) {
+    const double r = rho[x];
+    f = c[x] / (var[x] + r * r);  // marginal.py:150-153 summed over the ROI
+  } else if (rule == TAL_RULE_MMITL) {
+    f = c[x];
+  } else {
+    f = -c[x];  // tru_var/__init__.py:50
+  }
+  F[x] = accumulate ? F[x] + f : f;
+}
+
+__global__ void __launch_bounds__(256)
+itl_directed_kernel(const double* __restrict__ var, const double* __restrict__ cs,
+                    const double* __restrict__ rho, i64 n, int accumulate, double* __restrict__ F) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const double r = rho[x];
+  const double nz = r * r;
+  // diag(cov - Kxt^T Sigma^-1 Kxt) = var - ||L^-1 Kxt[:, x]||^2 (gaussian_distribution.py:36)
+  const double post_var = __dsub_rn(var[x], cs[x]);
+  // 0.5 * max(log(predictive / posterior_predictive), 0)  (itl.py:53-58);
+  // jnp.maximum propagates NaN
+  const double f = 0.5 * max_nan(log((var[x] + nz) / (post_var + nz)), 0.0);
+  F[x] = accumulate ? F[x] + f : f;
+}
+
+template <typename T, int RULE>
+static int launch_colsum_rows(const T* cov, i64 ld, i64 row0, i64 n_loc, i64 N, const i64* roi_idx,
+                              i64 m, const double* row_weight, const double* dinv, double p0,
+                              double p1, double* part, int n_split, cudaStream_t st) {
+  constexpr int VN = Vec16<T>::n;
+  dim3 grid((unsigned)((ld + 256 * VN - 1) / (256 * VN)), (unsigned)n_split);
+  colsum_rows_kernel<T, RULE, 4><<<grid, 256, 0, st>>>(cov, ld, row0, n_loc, N, roi_idx, m,
+                                                       row_weight, dinv, p0, p1, part);
+  return 0;
+}
+
+}  // namespace tal
+
+using namespace tal;
+
+extern "C" {
+
+int tal_score_itl_undirected(const double* var, const double* rho, int q, long long N, double* F,
+                             void* stream) {
+  TAL_ARG(var && rho && F && q >= 1 && N >= 1);
+  itl_undirected_kernel<<<(unsigned)((N + 255) / 256), 256, 0, as_stream(stream)>>>(var, rho, q, N,
+                                                                                   F);
+  TAL_LAUNCH_CHECK("tal_score_itl_undirected");
+  return TAL_OK;
+}
+
+int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                    long long N, const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* part, int n_split,
+                    double* c_out, int dtype, void* stream) {
+  TAL_ARG(cov && roi_idx && part && c_out && m >= 0 && n_split >= 1 && n_split <= 65535);
+  TAL_ARG(ld % 32 == 0 && ld >= N);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
+  cudaStream_t st = as_stream(stream);
+  double* dst = n_split == 1 ? c_out : part;
+#define TAL_ROWS(T, R)                                                                          \
+  launch_colsum_rows<T, R>((const T*)cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, \
+                           p1, dst, n_split, st)
+  if (dtype == TAL_F64) {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_ROWS(double, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_ROWS(double, TAL_RULE_MMITL); break;
+      default: TAL_ROWS(double, TAL_RULE_TRUVAR); break;
+    }
+  } else {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_ROWS(float, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_ROWS(float, TAL_RULE_MMITL); break;
+      default: TAL_ROWS(float, TAL_RULE_TRUVAR); break;
+    }
+  }
+#undef TAL_ROWS
+  TAL_LAUNCH_CHECK("tal_colsum_rows");
+  if (n_split > 1) {
+    sum_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(part, n_split, N, c_out);
+    TAL_LAUNCH_CHECK("tal_colsum_rows/sum_parts");
+  }
+  return TAL_OK;
+}
+
+int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
+                    const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* c_out, int dtype,
+                    void* stream) {
+  TAL_ARG(cov && roi_idx && c_out && m >= 0 && n_loc >= 0);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
+  if (n_loc == 0) return TAL_OK;
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)((n_loc + 7) / 8);
+#define TAL_COLS(T, R)                                                                        \
+  colsum_cols_kernel<T, R><<<grid, 256, 0, st>>>((const T*)cov, ld, n_loc, roi_idx, m,        \
+                                                 row_weight, dinv, p0, p1, c_out)
+  if (dtype == TAL_F64) {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_COLS(double, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_COLS(double, TAL_RULE_MMITL); break;
+      default: TAL_COLS(double, TAL_RULE_TRUVAR); break;
+    }
+  } else {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_COLS(float, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_COLS(float, TAL_RULE_MMITL); break;
+      default: TAL_COLS(float, TAL_RULE_TRUVAR); break;
+    }
+  }
+#undef TAL_COLS
+  TAL_LAUNCH_CHECK("tal_colsum_cols");
+  return TAL_OK;
+}
+
+int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,
+                  void* stream) {
+  TAL_ARG(var && roi_idx && out && m >= 0);
+  roi_trace_kernel<<<1, 256, 0, as_stream(stream)>>>(var, roi_idx, m, out);
+  TAL_LAUNCH_CHECK("tal_roi_trace");
+  return TAL_OK;
+}
+
+int tal_roi_weights(const double* var, const long long* roi_idx, long long m, int reciprocal,
+                    double* out, void* stream) {
+  TAL_ARG(var && roi_idx && out && m >= 0);
+  if (m == 0) return TAL_OK;
+  roi_weights_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(var, roi_idx, m,
+                                                                                reciprocal, out);
+  TAL_LAUNCH_CHECK("tal_roi_weights");
+  return TAL_OK;
+}
+
+int tal_pred_var_inv(const double* var, const double* rho, long long N, double* out,
+                     void* stream) {
+  TAL_ARG(var && rho && out && N >= 1);
+  pred_var_inv_kernel<<<(unsigned)((N + 255) / 256), 256, 0, as_stream(stream)>>>(var, rho, N, out);
+  TAL_LAUNCH_CHECK("tal_pred_var_inv");
+  return TAL_OK;
+}
+
+int tal_score_rows_finish(int rule, const double* c, const double* var, const double* rho,
+                          const double* tr, long long n, int accumulate, double* F,
+                          void* stream) {
+  TAL_ARG(c && F && n >= 0);
+  TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
+  TAL_ARG(rule > TAL_RULE_CTL || (var && rho));
+  TAL_ARG(rule != TAL_RULE_VTL || tr);
+  if (n == 0) return TAL_OK;
+  rows_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      rule, c, var, rho, tr, n, accumulate, F);
+  TAL_LAUNCH_CHECK("tal_score_rows_finish");
+  return TAL_OK;
+}
+
+int tal_score_itl_directed(const double* var, const double* cs, const double* rho,
+                           long long n, int accumulate, double* F, void* stream) {
+  TAL_ARG(var && cs && rho && F && n >= 0);
+  if (n == 0) return TAL_OK;
+  itl_directed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      var, cs, rho, n, accumulate, F);
+  TAL_LAUNCH_CHECK("tal_score_itl_directed");
+  return TAL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+"""Information-based transductive learning (reference: lib/algorithms/itl.py:11-60)."""
+import torch
+
+from lib.algorithms import DirectedDiscreteGreedyAlgorithm
+from lib.model.marginal import ROI, MarginalModel
+
+
+class ITL(DirectedDiscreteGreedyAlgorithm):
+    def F(self) -> torch.Tensor:
+        """:20-25 — undirected if the safe set is (scalar-wise) inside the ROI."""
+        roi = self.roi
+        if self.model.safe_set_is_subset_of(A=roi):
+            return _undirected(model=self.model)
+        return _directed(model=self.model, roi=roi)
+
+
+def _undirected(model: MarginalModel) -> torch.Tensor:
+    """:28-30 — sum_i log(1 + var_i / rho_i^2)."""
+    return model._gp.score_itl_undirected()
+
+
+def _directed(model: MarginalModel, roi) -> torch.Tensor:
+    """:33-60 — sum_i 0.5 max(log((var_i + rho_i^2)/(var_{i|A} + rho_i^2)), 0)
+    with var_{i|A} from gather -> Cholesky -> forward TRSM -> column sums of
+    squares (the reference forms the full N x N posterior and takes its diagonal)."""
+    if not isinstance(roi, ROI):
+        roi = ROI.from_points(model, roi)
+    return model._gp.score_itl_directed(roi.idx, roi.m)

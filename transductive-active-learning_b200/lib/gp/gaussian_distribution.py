@@ -1,0 +1,107 @@
+"""Multivariate Gaussian over the finite domain (reference:
+lib/gp/gaussian_distribution.py:13-121).
+
+The covariance lives in a `talgp.DeviceGP` slot (HBM-resident, row stride
+padded to 32 elements); `mean` / `covariance` / `variance` are views of that
+state.  `posterior` runs the gather -> small Cholesky -> rank-m streaming
+update kernels; like the reference it returns a NEW distribution unless
+`inplace=True` (which avoids the second N x N buffer the reference always
+pays for)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from lib._device import as_f64
+from talgp.engine import DeviceGP
+
+DEFAULT_JITTER = 1e-5  # gaussian_distribution.py:13
+
+
+class GaussianDistribution:
+    def __init__(self, mean, covariance, dtype: Optional[torch.dtype] = None):
+        mean = as_f64(mean).reshape(-1)
+        n = mean.shape[0]
+        cov = covariance if isinstance(covariance, torch.Tensor) else as_f64(covariance)
+        dtype = dtype or (cov.dtype if cov.dtype in (torch.float32, torch.float64) else torch.float64)
+        gp = DeviceGP(n, 1, dtype=dtype, device=mean.device)
+        gp.load_covariance(0, cov)
+        gp.mean[0].copy_(mean)
+        self._gp, self._slot = gp, 0
+
+    @classmethod
+    def _from_engine(cls, gp: DeviceGP, slot: int) -> "GaussianDistribution":
+        self = cls.__new__(cls)
+        self._gp, self._slot = gp, slot
+        return self
+
+    @classmethod
+    def initialize(cls, mean, kernel, X, dtype: torch.dtype = torch.float64):
+        """:69-71 — the Gram matrix is built in place on the device."""
+        X = as_f64(X)
+        gp = DeviceGP(X.shape[0], 1, dtype=dtype, device=X.device)
+        variance, lengthscale = kernel._gram_params()
+        gp.build_gram(0, kernel.kind, variance, lengthscale, X)
+        gp.mean[0].copy_(mean.vector(X))
+        return cls._from_engine(gp, 0)
+
+    @property
+    def n(self) -> int:
+        return self._gp.N
+
+    @property
+    def mean(self) -> torch.Tensor:
+        return self._gp.mean[self._slot]
+
+    @property
+    def covariance(self) -> torch.Tensor:
+        return self._gp.covariance_view(self._slot)
+
+    @property
+    def variance(self) -> torch.Tensor:
+        """:78-82 — maintained incrementally, bit-identical to diag(covariance)."""
+        return self._gp.var[self._slot]
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return torch.sqrt(self.variance)
+
+    def _clone(self) -> "GaussianDistribution":
+        src = self._gp
+        gp = DeviceGP(src.N, 1, dtype=src.dtype, device=src.device)
+        gp.cov[0].copy_(src.cov[self._slot])
+        gp.mean[0].copy_(src.mean[self._slot])
+        gp.var[0].copy_(src.var[self._slot])
+        return GaussianDistribution._from_engine(gp, 0)
+
+    def posterior(self, obs_idx, obs, obs_noise_std=None, jitter: float = DEFAULT_JITTER,
+                  inplace: bool = False) -> "GaussianDistribution":
+        """:100-121 — Gaussian posterior given m observations `obs` at `obs_idx`
+        with noise `obs_noise_std` (jitter^2 on the diagonal when None)."""
+        out = self if inplace else self._clone()
+        gp, i = out._gp, out._slot
+        obs_idx = torch.as_tensor(obs_idx).reshape(-1)
+        m = obs_idx.numel()
+        if m == 0:  # :23-24
+            return out
+        obs = as_f64(obs).reshape(-1)
+        if obs_noise_std is not None:
+            ns = as_f64(obs_noise_std).reshape(-1)
+            if ns.numel() == 1 and m > 1:
+                ns = ns.expand(m).contiguous()
+        else:
+            ns = None
+        gp.condition(i, obs_idx, obs, ns, jitter)
+        return out
+
+
+def compute_posterior_covariance(prior_covariance, obs_idx, obs_noise_std=None,
+                                 jitter: float = DEFAULT_JITTER) -> torch.Tensor:
+    """:40-55 — posterior covariance given observations at `obs_idx` (out of place)."""
+    n = prior_covariance.shape[0]
+    distr = GaussianDistribution(torch.zeros((n,), dtype=torch.float64), prior_covariance)
+    m = torch.as_tensor(obs_idx).numel()
+    distr.posterior(obs_idx, torch.zeros((m,), dtype=torch.float64), obs_noise_std, jitter,
+                    inplace=True)
+    return distr.covariance

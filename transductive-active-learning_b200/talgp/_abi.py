@@ -1,0 +1,120 @@
+"""ctypes binding of include/tal_b200.h (libtal_b200.so).
+
+There is no CPU fallback: importing this module without the built library, or
+calling into it on a machine whose GPU is not a B200-class (CC 10.x) device,
+fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtal_b200.so")
+
+# mirrors of the header's constants
+TAL_OK = 0
+TAL_MAX_Q = 16
+F64, F32 = 0, 1
+KERNEL_GAUSSIAN, KERNEL_LAPLACE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(5)
+RULE_VTL, RULE_CTL, RULE_MMITL, RULE_TRUVAR = range(4)
+ARGMAX_OK, ARGMAX_EMPTY_SAFE_SET, ARGMAX_ALL_NEG_INF, ARGMAX_ALL_NAN = 0, 2, 3, 4
+
+
+class ArgmaxResult(C.Structure):
+    _fields_ = [
+        ("idx", C.c_longlong),
+        ("val", C.c_double),
+        ("n_ties", C.c_longlong),
+        ("status", C.c_int),
+        ("flags", C.c_int),
+    ]
+
+
+class TalError(RuntimeError):
+    pass
+
+
+_p = C.c_void_p
+_ll = C.c_longlong
+_i = C.c_int
+_d = C.c_double
+
+# name -> (restype, argtypes); every symbol include/tal_b200.h declares
+SIGNATURES = {
+    "tal_abi_version": (_i, []),
+    "tal_last_error_string": (C.c_char_p, []),
+    "tal_launch_count": (_ll, []),
+    "tal_reset_launch_count": (None, []),
+    "tal_device_ok": (_i, []),
+    "tal_gram_stationary": (_i, [_i, _p, _ll, _p, _ll, _i, _d, _d, _p, _ll, _ll, _ll, _i, _p]),
+    "tal_nearest_index": (_i, [_p, _ll, _p, _ll, _i, _p, _p]),
+    "tal_extract_row": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _ll, _p, _p, _p, _i, _p]),
+    "tal_step_vectors": (_i, [_p, _p, _ll, _i, _p, _ll, _p, _ll, _i, _p, C.POINTER(_d), _p,
+                              _p, _p, _p, _p, _i, _p]),
+    "tal_rank1_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _i, _i, _p]),
+    "tal_gather_rows": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _ll, _i, _p]),
+    "tal_small_posterior_weights": (_i, [_p, _ll, _ll, _p, _i, _p, _d, _p, _p, _p, _p, _p]),
+    "tal_rankm_update": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p]),
+    "tal_bounds_masks": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "tal_mask_to_indices": (_i, [_p, _ll, _p, _p, _p]),
+    "tal_scalar_subset": (_i, [_p, _i, _ll, _ll, _p, _p, _p, _ll, _p, _p, _p]),
+    "tal_score_itl_undirected": (_i, [_p, _p, _i, _ll, _p, _p]),
+    "tal_colsum_rows": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p,
+                             _i, _p]),
+    "tal_colsum_cols": (_i, [_i, _p, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p]),
+    "tal_roi_trace": (_i, [_p, _p, _ll, _p, _p]),
+    "tal_roi_weights": (_i, [_p, _p, _ll, _i, _p, _p]),
+    "tal_pred_var_inv": (_i, [_p, _p, _ll, _p, _p]),
+    "tal_score_rows_finish": (_i, [_i, _p, _p, _p, _p, _ll, _i, _p, _p]),
+    "tal_gather_roi": (_i, [_p, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _i, _p]),
+    "tal_potrf_work_bytes": (_ll, [_ll]),
+    "tal_potrf_lower": (_i, [_p, _ll, _ll, _p, _p]),
+    "tal_trsm_lower": (_i, [_p, _ll, _ll, _p, _p, _ll, _ll, _p]),
+    "tal_colsumsq_dense": (_i, [_p, _ll, _ll, _ll, _p, _i, _p, _p]),
+    "tal_score_itl_directed": (_i, [_p, _p, _p, _ll, _i, _p, _p]),
+    "tal_argmax_scratch_bytes": (_ll, []),
+    "tal_masked_argmax": (_i, [_p, _p, _p, _i, _i, _ll, _p, _ll, _ll, _p, _p, _p]),
+    "tal_argmax_combine": (_i, [_p, _i, _p, _p]),
+    "tal_probe_fp64": (_i, [_i, _i, _i, _p, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libtal_b200.so and declare every signature.  Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TalError(
+            f"{LIB_PATH} is missing: build it with "
+            "`python transductive-active-learning_b200/build.py` (no CPU fallback exists)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().tal_last_error_string().decode()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != TAL_OK:
+        raise TalError(f"{what} failed with status {rc}: {last_error()}")
+
+
+def require_device() -> None:
+    """Fail loudly unless a B200-class GPU is usable."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise TalError("CUDA device required: the discrete-GP path has no CPU fallback")
+    if not load().tal_device_ok():
+        raise TalError(last_error())

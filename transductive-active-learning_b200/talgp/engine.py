@@ -1,0 +1,375 @@
+"""Device-resident state of q Gaussian processes over a finite domain, and the
+kernels that act on it (through the C ABI of include/tal_b200.h).
+
+This is the engine underneath the drop-in `lib.model` / `lib.algorithms`
+classes.  State layout in HBM (DESIGN.md "Data layout"):
+
+  cov   [q, n_loc, ld]  storage dtype (fp64 or fp32), row-major, ld = N rounded
+                        up to 32 elements, pad columns zero; rows
+                        [row0, row0 + n_loc) of every GP's N x N posterior
+                        covariance (one GPU: row0 = 0, n_loc = N)
+  mean, var, l, u, rho  [q, N] fp64, replicated on every shard
+  kbuf, wbuf            [q, ld] storage dtype: the observed row k and the
+                        weights w = (k / L) / L of the current step
+
+Reference correspondence: MarginalModel's `_means`, `_covariances`, `_l`,
+`_u` (lib/model/marginal.py:43-51); `var` replaces the strided
+`vmap(jnp.diag)` gather of `variances` (:103-106) and is kept bit-identical
+to the matrix diagonal by the update kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_DT = {torch.float64: _abi.F64, torch.float32: _abi.F32}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round_up(x: int, k: int) -> int:
+    return (x + k - 1) // k * k
+
+
+def nearest_index(domain: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
+    """get_indices(domain, A) (lib/utils.py:53-56): argmin_j ||domain[j] - A[k]||_2,
+    first minimum wins.  Returns int64 [m] on the device."""
+    _abi.require_device()
+    lib = _abi.load()
+    domain = domain.to(dtype=torch.float64).contiguous()
+    A = A.to(device=domain.device, dtype=torch.float64).contiguous()
+    m = A.shape[0]
+    out = torch.empty((m,), dtype=torch.int64, device=domain.device)
+    _abi.check(lib.tal_nearest_index(_ptr(domain), domain.shape[0], _ptr(A), m, domain.shape[1],
+                                     _ptr(out), _stream()), "tal_nearest_index")
+    return out
+
+
+class DeviceGP:
+    def __init__(self, N: int, q: int, dtype: torch.dtype = torch.float64,
+                 device: Optional[torch.device] = None, row0: int = 0,
+                 n_loc: Optional[int] = None, rank1_variant: int = 0):
+        _abi.require_device()
+        self.lib = _abi.load()
+        if q < 1 or q > _abi.TAL_MAX_Q:
+            raise ValueError(f"q must be in [1, {_abi.TAL_MAX_Q}]")
+        if dtype not in _DT:
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        self.N, self.q = int(N), int(q)
+        self.dtype, self.dt = dtype, _DT[dtype]
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda", torch.cuda.current_device())
+        self.row0 = int(row0)
+        self.n_loc = self.N if n_loc is None else int(n_loc)
+        self.ld = round_up(self.N, 32)
+        self.rank1_variant = rank1_variant
+        dev = self.device
+        self.cov = torch.zeros((q, self.n_loc, self.ld), dtype=dtype, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.mean = torch.zeros((q, N), **f64)
+        self.var = torch.zeros((q, N), **f64)
+        self.l = torch.zeros((q, N), **f64)
+        self.u = torch.zeros((q, N), **f64)
+        self.rho = torch.zeros((q, N), **f64)
+        self.kbuf = torch.zeros((q, self.ld), dtype=dtype, device=dev)
+        self.wbuf = torch.zeros((q, self.ld), dtype=dtype, device=dev)
+        self.scal = torch.zeros((q,), **f64)
+        self._argmax_scratch = torch.zeros((int(self.lib.tal_argmax_scratch_bytes()),),
+                                           dtype=torch.uint8, device=dev)
+        self._result = torch.zeros((4,), dtype=torch.int64, device=dev)  # tal_argmax_result
+        self._result_host = torch.zeros((4,), dtype=torch.int64).pin_memory()
+        self._y_host = torch.zeros((q,), dtype=torch.float64).pin_memory()
+        self._y_dev = torch.zeros((q,), **f64)
+        self._ws = {}  # named scratch tensors, grown on demand
+
+    # ------------------------------------------------------------------ util
+    def _scratch(self, name: str, shape, dtype=torch.float64) -> torch.Tensor:
+        t = self._ws.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty((n,), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    @property
+    def cov_stride_q(self) -> int:
+        return self.n_loc * self.ld
+
+    def covariance_view(self, i: int) -> torch.Tensor:
+        """[n_loc, N] view of GP i's covariance rows (no copy)."""
+        return self.cov[i, :, : self.N]
+
+    def launch_count(self) -> int:
+        return int(self.lib.tal_launch_count())
+
+    # ------------------------------------------------------------ construction
+    def build_gram(self, i: int, kind: int, variance: float, lengthscale: float,
+                   domain: torch.Tensor) -> None:
+        """cov[i] = K(domain, domain)[row0:row0+n_loc] and var[i] = its diagonal.
+        (Kernel.covariance, lib/gp/kernels/base.py:24-25.)"""
+        assert domain.dtype == torch.float64 and domain.is_contiguous()
+        n, d = domain.shape
+        assert n == self.N
+        _abi.check(self.lib.tal_gram_stationary(
+            kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
+            _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
+            "tal_gram_stationary")
+        # diagonal of a stationary kernel: k(x, x), evaluated by the same kernel
+        # on a one-row problem per point is wasteful; the diagonal entries of
+        # the shard are copied instead and completed by the caller when sharded.
+        if self.n_loc == self.N:
+            self.var[i].copy_(torch.diagonal(self.cov[i, :, : self.N]).to(torch.float64))
+        else:
+            sl = slice(self.row0, self.row0 + self.n_loc)
+            self.var[i, sl].copy_(
+                torch.diagonal(self.cov[i, :, self.row0:self.row0 + self.n_loc]).to(torch.float64))
+
+    def load_covariance(self, i: int, cov) -> None:
+        """Upload a full N x N covariance (host or device) into shard i."""
+        src = torch.as_tensor(cov)
+        rows = src[self.row0:self.row0 + self.n_loc]
+        self.cov[i, :, : self.N].copy_(rows.to(device=self.device, dtype=self.dtype))
+        self.var[i].copy_(torch.diagonal(src).to(device=self.device, dtype=torch.float64))
+        if self.dtype != torch.float64:  # keep var == diag(cov) in the storage precision
+            self.var[i].copy_(self.var[i].to(self.dtype).to(torch.float64))
+
+    def init_bounds(self, beta: Sequence[float]) -> None:
+        """l = mean - beta*stddev, u = mean + beta*stddev (marginal.py:160-164)."""
+        b = torch.as_tensor(np.asarray(beta, dtype=np.float64), device=self.device)[:, None]
+        sd = torch.sqrt(self.var)
+        self.l.copy_(self.mean - b * sd)
+        self.u.copy_(self.mean + b * sd)
+
+    # ------------------------------------------------------------------ update
+    def extract_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
+        _abi.check(self.lib.tal_extract_row(
+            _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+            _ptr(idx_dev), int(idx_host), _ptr(self.mean), _ptr(self.kbuf), _ptr(self.scal),
+            self.dt, _stream()), "tal_extract_row")
+
+    def step_vectors(self, idx_dev: Optional[torch.Tensor], idx_host: int, y_dev: torch.Tensor,
+                     y_stride: int, y_gather: bool, beta: Sequence[float]) -> None:
+        b = (C.c_double * self.q)(*[float(x) for x in beta])
+        _abi.check(self.lib.tal_step_vectors(
+            _ptr(self.kbuf), _ptr(self.wbuf), self.N, self.q, _ptr(idx_dev), int(idx_host),
+            _ptr(y_dev), int(y_stride), int(bool(y_gather)), _ptr(self.rho), b, _ptr(self.scal),
+            _ptr(self.mean), _ptr(self.var), _ptr(self.l), _ptr(self.u), self.dt, _stream()),
+            "tal_step_vectors")
+
+    def rank1_update(self, variant: Optional[int] = None) -> None:
+        _abi.check(self.lib.tal_rank1_update(
+            _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+            _ptr(self.kbuf), _ptr(self.wbuf), self.dt,
+            self.rank1_variant if variant is None else variant, _stream()), "tal_rank1_update")
+
+    def observe(self, idx, y, beta: Sequence[float], y_gather: bool = False,
+                y_stride: int = 1, allreduce=None) -> None:
+        """One observation at domain index `idx` (python int or 1-element int64
+        device tensor) with values y[q] (host sequence, or device tensor; with
+        y_gather a device table [q, y_stride] indexed at idx).
+        `allreduce(t)` completes kbuf across shards (sum; only the owner's is non-zero)."""
+        if isinstance(idx, torch.Tensor):
+            idx_dev, idx_host = idx, 0
+        else:
+            idx_dev, idx_host = None, int(idx)
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            y_dev = y
+        else:
+            self._y_host.copy_(torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1)))
+            self._y_dev.copy_(self._y_host, non_blocking=True)
+            y_dev = self._y_dev
+        self.extract_row(idx_dev, idx_host)
+        if allreduce is not None:
+            allreduce(self.kbuf)
+        self.step_vectors(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
+        self.rank1_update()
+
+    def condition(self, i: int, obs_idx: torch.Tensor, y: torch.Tensor,
+                  noise_std: Optional[torch.Tensor], jitter: float = 1e-5,
+                  allreduce=None) -> None:
+        """GP i <- posterior given m observations (GaussianDistribution.posterior,
+        lib/gp/gaussian_distribution.py:100-121), in chunks of <= 64 observations
+        (conditioning chunk after chunk is the same posterior)."""
+        m_total = int(obs_idx.numel())
+        if m_total == 0:  # :23-24 short-circuit
+            return
+        obs_idx = obs_idx.to(device=self.device, dtype=torch.int64).contiguous()
+        y = y.to(device=self.device, dtype=torch.float64).contiguous()
+        if noise_std is not None:
+            noise_std = noise_std.to(device=self.device, dtype=torch.float64).contiguous()
+        ldb = self.ld
+        for s in range(0, m_total, 64):
+            e = min(m_total, s + 64)
+            m = e - s
+            B = self._scratch("cond_B", (m, ldb))
+            W = self._scratch("cond_W", (m, ldb))
+            oi = obs_idx[s:e]
+            _abi.check(self.lib.tal_gather_rows(
+                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(oi), m, _ptr(B),
+                ldb, self.dt, _stream()), "tal_gather_rows")
+            if allreduce is not None:
+                allreduce(B)
+            _abi.check(self.lib.tal_small_posterior_weights(
+                _ptr(B), ldb, self.N, _ptr(oi), m,
+                _ptr(noise_std[s:e]) if noise_std is not None else None, float(jitter),
+                _ptr(y[s:e]), _ptr(W), _ptr(self.mean[i]), _ptr(self.var[i]), _stream()),
+                "tal_small_posterior_weights")
+            _abi.check(self.lib.tal_rankm_update(
+                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(B), _ptr(W), ldb,
+                m, self.dt, _stream()), "tal_rankm_update")
+        if self.dtype != torch.float64:
+            self.var[i].copy_(self.var[i].to(self.dtype).to(torch.float64))
+
+    # ------------------------------------------------------------------- masks
+    def bounds_masks(self, first_constraint: int, op_safe: Optional[torch.Tensor] = None,
+                     want_pm: bool = True, want_pe: bool = True):
+        """(pess, opt, pm, pe, max_l) — marginal.py:171-224.  Masks are uint8 [N]."""
+        N = self.N
+        u8 = dict(dtype=torch.uint8, device=self.device)
+        pess = torch.empty((N,), **u8)
+        opt = torch.empty((N,), **u8)
+        pm = torch.empty((N,), **u8) if want_pm else None
+        pe = torch.empty((N,), **u8) if want_pe else None
+        max_l = torch.empty((1,), dtype=torch.float64, device=self.device)
+        _abi.check(self.lib.tal_bounds_masks(
+            _ptr(self.l), _ptr(self.u), self.q, int(first_constraint), N, _ptr(op_safe),
+            _ptr(pess), _ptr(opt), _ptr(pm), _ptr(pe), _ptr(max_l), _stream()),
+            "tal_bounds_masks")
+        return pess, opt, pm, pe, max_l
+
+    def mask_to_indices(self, mask: torch.Tensor):
+        """(idx[N] int64 (first `count` valid, ascending), count[1] int64 device)."""
+        idx = torch.empty((self.N,), dtype=torch.int64, device=self.device)
+        count = torch.empty((1,), dtype=torch.int64, device=self.device)
+        _abi.check(self.lib.tal_mask_to_indices(_ptr(mask), mask.numel(), _ptr(idx), _ptr(count),
+                                                _stream()), "tal_mask_to_indices")
+        return idx, count
+
+    # ----------------------------------------------------------------- scoring
+    def score_itl_undirected(self) -> torch.Tensor:
+        F = torch.empty((self.N,), dtype=torch.float64, device=self.device)
+        _abi.check(self.lib.tal_score_itl_undirected(_ptr(self.var), _ptr(self.rho), self.q,
+                                                     self.N, _ptr(F), _stream()),
+                   "tal_score_itl_undirected")
+        return F
+
+    def _n_split(self, m: int) -> int:
+        col_tiles = max(1, self.ld * (8 if self.dtype == torch.float64 else 4) // 4096)
+        return int(max(1, min(64, m, -(-1184 // col_tiles))))
+
+    def score_rows(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0,
+                   sharded_cols: bool = False) -> torch.Tensor:
+        """F over this shard's candidates for the row-reduce rules (VTL, CTL,
+        MM-ITL, TruVar).  One GPU: F is [N]; row-sharded with `sharded_cols`:
+        F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
+        lib = self.lib
+        N = self.N
+        n_out = self.n_loc if sharded_cols else N
+        off = self.row0 if sharded_cols else 0
+        F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
+        c = self._scratch("score_c", (n_out,))
+        tr = self._scratch("score_tr", (1,))
+        need_w = rule != _abi.RULE_VTL
+        need_dinv = rule in (_abi.RULE_MMITL, _abi.RULE_TRUVAR)
+        w = self._scratch("score_w", (max(m, 1),)) if need_w else None
+        dinv = self._scratch("score_dinv", (N,)) if need_dinv else None
+        n_split = self._n_split(m)
+        part = self._scratch("score_part", (n_split, N)) if not sharded_cols else None
+        if m == 0:
+            F.zero_()
+            if rule == _abi.RULE_VTL:
+                F.neg_()
+            return F
+        for i in range(self.q):
+            if need_w:
+                _abi.check(lib.tal_roi_weights(_ptr(self.var[i]), _ptr(roi_idx), m,
+                                               0 if rule == _abi.RULE_TRUVAR else 1, _ptr(w),
+                                               _stream()), "tal_roi_weights")
+            if need_dinv:
+                _abi.check(lib.tal_pred_var_inv(_ptr(self.var[i]), _ptr(self.rho[i]), N,
+                                                _ptr(dinv), _stream()), "tal_pred_var_inv")
+            pp0 = float(p0[i]) if p0 is not None else 0.0
+            if sharded_cols:
+                _abi.check(lib.tal_colsum_cols(
+                    rule, _ptr(self.cov[i]), self.ld, self.n_loc, _ptr(roi_idx), m, _ptr(w),
+                    _ptr(dinv[off:]) if dinv is not None else None, pp0, float(p1), _ptr(c),
+                    self.dt, _stream()), "tal_colsum_cols")
+            else:
+                _abi.check(lib.tal_colsum_rows(
+                    rule, _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m,
+                    _ptr(w), _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt,
+                    _stream()), "tal_colsum_rows")
+            if rule == _abi.RULE_VTL:
+                _abi.check(lib.tal_roi_trace(_ptr(self.var[i]), _ptr(roi_idx), m, _ptr(tr),
+                                             _stream()), "tal_roi_trace")
+            _abi.check(lib.tal_score_rows_finish(
+                rule, _ptr(c), _ptr(self.var[i, off:]), _ptr(self.rho[i, off:]), _ptr(tr), n_out,
+                1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
+        return F
+
+    def cond_var_sumsq(self, i: int, roi_idx: torch.Tensor, m: int,
+                       jitter: float = 1e-5) -> torch.Tensor:
+        """cs[x] = || L^-1 cov_i[A, x] ||^2 with L = chol(cov_i[A, A] + jitter^2 I):
+        the part of compute_posterior_covariance's diagonal that directed ITL
+        uses (itl.py:41-48).  One GPU (full rows)."""
+        assert self.n_loc == self.N, "conditioning needs the full rows on this device"
+        lib = self.lib
+        m_pad = round_up(m, 128)
+        ncols = round_up(self.N, 64)
+        ldb = ncols
+        S = self._scratch("cv_S", (m_pad, m_pad))
+        B = self._scratch("cv_B", (m_pad, ldb))
+        work = self._scratch("cv_work", (int(lib.tal_potrf_work_bytes(m_pad)) // 8,))
+        _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m, m_pad,
+                                      float(jitter), _ptr(S), m_pad, _ptr(B), ldb, self.dt,
+                                      _stream()), "tal_gather_roi")
+        _abi.check(lib.tal_potrf_lower(_ptr(S), m_pad, m_pad, _ptr(work), _stream()),
+                   "tal_potrf_lower")
+        _abi.check(lib.tal_trsm_lower(_ptr(S), m_pad, m_pad, _ptr(work), _ptr(B), ldb, ncols,
+                                      _stream()), "tal_trsm_lower")
+        n_split = int(max(1, min(64, m_pad // 64, -(-1184 // max(1, ncols // 512)))))
+        part = self._scratch("cv_part", (n_split, ncols))
+        cs = self._scratch("cv_cs", (ncols,))
+        _abi.check(lib.tal_colsumsq_dense(_ptr(B), ldb, m_pad, ncols, _ptr(part), n_split,
+                                          _ptr(cs), _stream()), "tal_colsumsq_dense")
+        return cs[: self.N]
+
+    def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5) -> torch.Tensor:
+        F = torch.empty((self.N,), dtype=torch.float64, device=self.device)
+        for i in range(self.q):
+            cs = self.cond_var_sumsq(i, roi_idx, m, jitter)
+            _abi.check(self.lib.tal_score_itl_directed(
+                _ptr(self.var[i]), _ptr(cs), _ptr(self.rho[i]), self.N, 1 if i > 0 else 0,
+                _ptr(F), _stream()), "tal_score_itl_directed")
+        return F
+
+    # ------------------------------------------------------------------ argmax
+    def masked_argmax(self, F: torch.Tensor, safe: Optional[torch.Tensor], first_constraint: int,
+                      sample: Optional[torch.Tensor], idx_offset: int = 0,
+                      l_offset: int = 0) -> torch.Tensor:
+        """Enqueue the masked arg-max; returns the device result record
+        (int64[4] view of tal_argmax_result)."""
+        n = F.numel()
+        _abi.check(self.lib.tal_masked_argmax(
+            _ptr(F), _ptr(safe), _ptr(self.l[:, l_offset:]) if safe is None else None, self.q,
+            int(first_constraint), self.N, _ptr(sample), n, int(idx_offset),
+            _ptr(self._argmax_scratch), _ptr(self._result), _stream()), "tal_masked_argmax")
+        return self._result
+
+    def read_result(self, result: Optional[torch.Tensor] = None) -> _abi.ArgmaxResult:
+        """Device -> host read of an arg-max record (synchronises the stream)."""
+        r = self._result if result is None else result
+        self._result_host.copy_(r, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return _abi.ArgmaxResult.from_buffer_copy(self._result_host.numpy().tobytes())
