@@ -1,0 +1,439 @@
+"""Benchmark of the discrete-GP hot path (BASELINE.json: "BO steps/s (rank-1
+update + ITL argmax) at N=65k; HBM GB/s vs B200 peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--conditioning incremental|recompute] [--workload c3|c3_small]
+
+One step = directed-ITL score over all N candidates (fixed target set A,
+|A| = m) -> safe-set-masked arg-max -> rank-1 posterior update of the N x N
+covariance.  Workload "c3" is BASELINE.json configs[2]: N = 65,536, m = 4,096,
+d = 4, Matérn-5/2 (l = 0.25), q = 1, rho = 0.1, fp64, synthetic data.
+
+  value  device-resident loop (index, observation table and state in HBM, no
+         host synchronisation inside the timed region)
+  e2e    the same steps through the drop-in API `ITL.step(f)` with a HOST black
+         box f: per step the arg-max record and the selected point are read
+         back (D2H) and the observation is copied in from pinned memory (H2D)
+
+With --gpus N > 1 (launched by torchrun, one rank per GPU) the covariance is
+row-sharded over the ranks (talgp/dist.py); the total problem is fixed
+("scaling": "strong").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "transductive-active-learning_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "c3": dict(N=65536, m=4096, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=16),
+    "c3_small": dict(N=4096, m=256, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=8),
+}
+METRIC = "BO steps/s (rank-1 update + ITL argmax) at N=65k"
+UNIT = "steps/s"
+
+
+# --------------------------------------------------------------------------- data
+def make_problem(w):
+    """Synthetic inputs of the named shape: one uniform point per cell of a
+    grid^d lattice on [0,1)^d (on the bare lattice the reference's scalar-wise
+    subset test, lib/utils.py:65-71, would pick the UNdirected rule), a fixed
+    target set A, and a table of noisy observations."""
+    g, d, N = w["grid"], w["d"], w["N"]
+    rng = np.random.default_rng(0)
+    axes = np.meshgrid(*([np.arange(g) / g] * d), indexing="ij")
+    domain = np.stack(axes, -1).reshape(-1, d)[:N] + rng.random((N, d)) / g
+    A = np.sort(rng.choice(N, w["m"], replace=False))
+    r1 = np.random.default_rng(1)
+    noise = r1.standard_normal(N)
+    table = (np.sin(3.0 * domain.sum(axis=1)) + w["rho"] * noise)[None, :]
+    return domain, A, table
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# -------------------------------------------------------------------- CPU baseline
+def cpu_oracle_sample(w, n_s, steps, warmup=1):
+    """Times the NumPy oracle (the reference's algorithm as written) on a bounded
+    sample of the workload: the same problem family at N_s candidates with
+    m_s = N_s / 16 targets, and extrapolates each phase to the full size by its
+    complexity (directed ITL ~ N^2 m, posterior update and sample-region mask ~ N^2)."""
+    import oracle as O
+    ws = dict(w, N=n_s, m=max(8, n_s * w["m"] // w["N"]), grid=max(2, int(round(n_s ** (1.0 / w["d"])))))
+    while ws["grid"] ** ws["d"] < n_s:
+        ws["grid"] += 1
+    domain, A, table = make_problem(ws)
+    noise = O.HomoscedasticNoise(1, np.array([w["rho"]]))
+    distrs = O.prior_distr(noise, domain, np.zeros((0, w["d"])), np.zeros((1, 0)),
+                           [O.Matern52(lengthscale=w["lengthscale"])], [O.ZeroMean()])
+    model = O.MarginalModel(0, domain, distrs, beta=np.array([w["beta"]]), noise_rate=noise)
+    t_itl = t_mask = t_upd = 0.0
+    cpu0 = time.process_time()
+    wall0 = time.perf_counter()
+    done = 0
+    for t in range(warmup + steps):
+        a = time.perf_counter()
+        F = O.itl_directed(model, roi_idx=A)             # lib/algorithms/itl.py:33-60 (full N x N)
+        b = time.perf_counter()
+        mask = O.get_mask(model.domain, model.domain)     # lib/algorithms/__init__.py:80
+        F = F.copy(); F[~mask] = -np.inf
+        c = time.perf_counter()
+        idx = model.objective_argmax_index(F)
+        model.step_idx(np.array([idx]), table[:, [idx]], np.array([[w["rho"]]]))  # marginal.py:350-368
+        e = time.perf_counter()
+        if t >= warmup:
+            t_itl += b - a; t_mask += c - b; t_upd += e - c; done += 1
+    wall = time.perf_counter() - wall0
+    cpu = time.process_time() - cpu0
+    sN = (w["N"] / ws["N"]) ** 2
+    sM = w["m"] / ws["m"]
+    per_step_full = (t_itl * sN * sM + t_mask * sN + t_upd * sN) / done
+    per_step_sample = (t_itl + t_mask + t_upd) / done
+    return dict(
+        value=1.0 / per_step_full, unit=UNIT, cores=os.cpu_count(), kind="port",
+        sample=(f"NumPy oracle, {done} steps at N_s={ws['N']}, m_s={ws['m']} (same kernel/d/rho): "
+                f"{per_step_sample * 1e3:.1f} ms/step measured (ITL {t_itl / done * 1e3:.1f}, mask "
+                f"{t_mask / done * 1e3:.1f}, update+argmax {t_upd / done * 1e3:.1f}); extrapolated to N={w['N']}, "
+                f"m={w['m']} by N^2*m / N^2 / N^2 -> {per_step_full:.1f} s/step. The reference as written "
+                f"cannot run the full size (N x N x d temporary, 3 x 34 GB matrices)."),
+        measured_ms_per_step_at_sample=per_step_sample * 1e3, wall_s=wall, process_time_s=cpu)
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's own CPU algorithm (oracle port: the
+    JAX reference cannot be installed here) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = args.steps + args.warmup
+    budget = 150.0 / max(1, total)  # seconds per step so that the run ends within minutes
+    # calibrate at a small size, then pick the largest sample that fits the budget (cost ~ N^3)
+    t0 = time.perf_counter()
+    cpu_oracle_sample(w, 1024, 1, 0)
+    t1024 = time.perf_counter() - t0
+    n_s = 1024
+    for cand in (2048, 4096, 8192):
+        if t1024 * (cand / 1024.0) ** 3 <= budget:
+            n_s = cand
+    res = cpu_oracle_sample(w, n_s, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, w, 1),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, w, world):
+    return {
+        "workload": (f"BASELINE configs[2]: synthetic transductive ITL, N={w['N']} candidates, target set "
+                     f"m={w['m']}, d={w['d']} Matern-5/2 (l={w['lengthscale']}), q=1, rho={w['rho']}, fp64"),
+        "name": args.workload, "N": w["N"], "m": w["m"], "d": w["d"], "q": 1,
+        "conditioning": args.conditioning,
+        "l2": "inputs larger than L2 (covariance %.1f GB per GPU >> 126 MB): no flush needed"
+              % (w["N"] * w["N"] * 8 / world / 1e9),
+        "parallelism": "1 GPU" if world == 1 else f"covariance row-sharded over {world} GPUs",
+    }
+
+
+# ----------------------------------------------------------------------- GPU arm
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from talgp import _abi
+    from talgp.engine import DeviceGP  # noqa: F401
+    lib = _abi.load()
+    _abi.require_device()
+    domain, A, table = make_problem(w)
+    N, m, rho, beta = w["N"], w["m"], w["rho"], [w["beta"]]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+
+    clocks = ClockSampler(local)
+
+    if world == 1:
+        from lib.algorithms import index_roi_constructor
+        from lib.algorithms.itl import ITL
+        from lib.function import Function
+        from lib.gp.kernels import stationary
+        from lib.gp.means import ZeroMean
+        from lib.gp.prior import prior_distr
+        from lib.model.marginal import MarginalModel
+        from lib.noise import HomoscedasticNoise
+
+        def build_model():
+            nz = HomoscedasticNoise(1, np.array([rho]))
+            distrs = prior_distr(nz, domain, np.zeros((0, w["d"])), np.zeros((1, 0)),
+                                 [stationary.Matern52(lengthscale=w["lengthscale"])], [ZeroMean()])
+            model = MarginalModel(0, domain, distrs, beta=np.array(beta), noise_rate=nz)
+            alg = ITL(model, index_roi_constructor(A), conditioning=args.conditioning)
+            alg.sample_mask()  # static; computed once (lib/algorithms/__init__.py:80)
+            return model, alg
+
+        model, alg = build_model()
+        gp = model._gp
+        table_dev = torch.as_tensor(table, device=dev)
+        roi = alg.roi
+        inc = args.conditioning == "incremental"
+
+        # ---- device-resident loop (value) -----------------------------------
+        ev = []
+
+        def dev_step(record):
+            F = gp.score_itl_directed(roi.idx, roi.m, incremental=inc, roi_key=roi)
+            res = gp.masked_argmax(F, None, model.first_constraint, alg.sample_mask())
+            idx_dev = res[0:1]  # tal_argmax_result.idx
+            gp.extract_row(idx_dev)
+            gp.step_vectors(idx_dev, 0, table_dev, N, True, beta)
+            if gp._cond is not None and gp._cond["valid"]:
+                gp._cond_downdate(idx_dev, 0)
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gp.rank1_update()
+                e1.record()
+                ev.append((e0, e1))
+            else:
+                gp.rank1_update()
+
+        for _ in range(args.warmup):
+            dev_step(False)
+        torch.cuda.synchronize()
+        lib.tal_reset_launch_count()
+        clocks.start()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            dev_step(True)
+        t1.record()
+        torch.cuda.synchronize()
+        total_ms = t0.elapsed_time(t1)
+        launches = int(lib.tal_launch_count())
+        rank1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        status = gp.read_result().status
+        assert status == 0, f"arg-max status {status}"
+
+        # ---- end to end through the drop-in API with a host black box ---------
+        class HostFunction(Function):
+            q, first_constraint = 1, 1
+
+            def observe(self, X):  # X: [1, d] device tensor -> D2H; returns host array [q, 1]
+                x = X.cpu().numpy()
+                i = model.last_argmax.idx
+                noise = table[0, i] - np.sin(3.0 * domain[i].sum())  # the pre-drawn noise of point i
+                return np.array([[np.sin(3.0 * x.sum()) + noise]])
+
+        f = HostFunction()
+        for _ in range(max(1, min(args.warmup, 3))):
+            alg.step(f)
+        torch.cuda.synchronize()
+        e2e_steps = args.steps
+        w0 = time.perf_counter()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(e2e_steps):
+            out = alg.step(f)
+        fmax = float(out["F_max"])  # D2H read of the step's result
+        a1.record()
+        torch.cuda.synchronize()
+        e2e_ms = max(a0.elapsed_time(a1), (time.perf_counter() - w0) * 1e3)
+        clk = clocks.stop()
+        assert np.isfinite(fmax)
+        h2d = 8 * model.q
+        d2h = 32 + 8 * w["d"] + 4  # arg-max record + selected point + subset-test flag
+        value = args.steps / (total_ms / 1e3)
+        e2e_value = e2e_steps / (e2e_ms / 1e3)
+        alg_bytes = 2.0 * model.q * N * gp.ld * 8
+        achieved = alg_bytes / (rank1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, w, 1),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": launches,
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "roofline": {"kernel": "rank1_update (tal_rank1_update)", "bound": "hbm", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rank1_ms,
+                         "share_of_step": rank1_ms / (total_ms / args.steps)},
+        }
+        # the recompute-every-step figure beside the incremental one (and vice versa)
+        if args.both:
+            other = "recompute" if inc else "incremental"
+            del model, alg, gp, roi
+            torch.cuda.empty_cache()
+            sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(max(3, args.steps // 4)),
+                                  "--warmup", "2", "--conditioning", other, "--workload", args.workload,
+                                  "--no-both", "--no-cpu"], capture_output=True, text=True)
+            try:
+                o = json.loads(sub.stdout.strip().splitlines()[-1])
+                line["value_" + other] = {"value": o["value"], "ms_per_step": o["ms_per_step"],
+                                          "e2e": o["e2e"]["value"]}
+            except Exception as exc:  # pragma: no cover
+                line["value_" + other] = {"error": str(exc), "stderr": sub.stderr[-300:]}
+        if not args.no_cpu:
+            line["cpu_baseline"] = {k: v for k, v in cpu_oracle_sample(w, args.cpu_sample_n, 3, 1).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---- N > 1: row-sharded -------------------------------------------------
+    from talgp.dist import ShardedITLBench
+    bench = ShardedITLBench(domain, A, table, w, world, rank, dev, args.conditioning)
+    for _ in range(args.warmup):
+        bench.step(False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    lib.tal_reset_launch_count()
+    clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.steps):
+        bench.step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    total_ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    rank1_ms = torch.tensor([bench.rank1_ms()], device=dev, dtype=torch.float64)
+    dist.all_reduce(rank1_ms, op=dist.ReduceOp.MAX)
+    launches = int(lib.tal_launch_count())
+    e2e_ms = bench.e2e(args.steps)
+    clk = clocks.stop()
+    if rank == 0:
+        total_ms, rank1_ms = float(total_ms), float(rank1_ms)
+        alg_bytes = 2.0 * bench.gp.n_loc * bench.gp.ld * 8
+        achieved = alg_bytes / (rank1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, w, world),
+            "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8,
+                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "roofline": {"kernel": "rank1_update (tal_rank1_update), per GPU, max over ranks", "bound": "hbm",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                         "ms_per_launch": rank1_ms, "share_of_step": rank1_ms / (total_ms / args.steps)},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--conditioning", default="incremental", choices=["incremental", "recompute"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-n", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-both", dest="both", action="store_false",
+                    help="do not also time the other conditioning mode")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            args.no_cpu = True
+            args.both = False
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -236,6 +236,14 @@ int tal_score_rows_finish(int rule, const double* c, const double* var, const do
 int tal_gather_roi(const void* cov, long long ld, long long N, const long long* roi_idx,
                    long long m, long long m_pad, double jitter, double* S, long long lds,
                    double* B, long long ldb, int dtype, void* stream);
+/* row-sharded gather: B[j][x] = cov[roi[j]][row0 + x] read through the symmetric
+ * entry cov_loc[x][roi[j]] ([m_pad][ldb], ncols >= n_loc columns written, pads
+ * zero); S receives the rows whose roi[j] this shard owns (+ the identity pad
+ * on the shard with row0 = 0) and zeros elsewhere: a sum over shards gives S. */
+int tal_gather_roi_sharded(const void* cov, long long ld, long long row0, long long n_loc,
+                           const long long* roi_idx, long long m, long long m_pad, double jitter,
+                           double* S, long long lds, double* B, long long ldb, long long ncols,
+                           int dtype, void* stream);
 long long tal_potrf_work_bytes(long long m_pad);
 int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void* stream);
 int tal_trsm_lower(const double* L, long long lds, long long m_pad, const void* work, double* B,
@@ -244,6 +252,27 @@ int tal_colsumsq_dense(const double* V, long long ldv, long long m, long long n_
                        double* part, int n_split, double* out, void* stream);
 int tal_score_itl_directed(const double* var, const double* cs, const double* rho,
                            long long n, int accumulate, double* F, void* stream);
+
+/* ---- incremental conditioning for a fixed ROI ---------------------------
+ * Beyond the reference (which re-runs the m x m Cholesky and the m x N solves
+ * of lib/algorithms/itl.py:41-48 at every step): when the ROI is unchanged,
+ * V = L^-1 cov[A,:] and cs follow from the previous step's by an exact rank-1
+ * downdate (csrc/condinc.cu).  Per observation at index idx:
+ * tal_cond_extract_col: pcol[j] = V[j][idx - col0] if this shard holds that
+ *   column (else 0, so that a sum over shards broadcasts it).
+ * tal_cond_update: V <- T^-1 (V - pcol w^T), cs[x] = sum_j V[j][x]^2, with
+ *   T = chol(I - p p^T), p = pcol / sqrt(k[idx] + rho[idx]^2); kbuf_i, wbuf_i,
+ *   rho_i are GP i's rows of kbuf / wbuf / rho as left by tal_step_vectors.
+ *   V is [m_pad][ncols] (row stride ldv) and holds global columns
+ *   [col0, col0 + n_valid); coef_scratch: tal_cond_coef_bytes(m_pad).       */
+int tal_cond_extract_col(const double* V, long long ldv, long long m_pad, long long col0,
+                         long long ncols, const long long* idx_dev, long long idx_host,
+                         double* pcol, void* stream);
+int tal_cond_update(double* V, long long ldv, long long m_pad, long long ncols, long long n_valid,
+                    long long col0, const double* pcol, const void* kbuf_i, const void* wbuf_i,
+                    const double* rho_i, const long long* idx_dev, long long idx_host,
+                    void* coef_scratch, double* cs, int dtype, void* stream);
+long long tal_cond_coef_bytes(long long m_pad);
 
 /* ---- masked arg-max -----------------------------------------------------
  * Replaces DiscreteGreedyAlgorithm._step's sample-region masking

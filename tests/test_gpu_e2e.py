@@ -158,7 +158,8 @@ def test_c2_2d_safe_bo_vtl(cuda, rule):
     assert steps == 15 and agree >= 13
 
 
-def test_c3_fixed_roi_itl_matern52_d4(cuda):
+@pytest.mark.parametrize("conditioning", ["recompute", "incremental"])
+def test_c3_fixed_roi_itl_matern52_d4(cuda, conditioning):
     """Config 3 scaled down: transductive ITL with a fixed target set, d = 4
     Matérn-5/2, unconstrained (always the directed rule), default sample region."""
     from lib.algorithms import index_roi_constructor
@@ -177,7 +178,7 @@ def test_c3_fixed_roi_itl_matern52_d4(cuda):
     mo, mc = _build_pair(domain, [O.Matern52(lengthscale=0.25)], [stationary.Matern52(lengthscale=0.25)],
                          beta=[1.0], rho=[0.1], X0=np.zeros((0, 4)), y0=np.zeros((1, 0)), fc_obj=False)
     alg_o = O.ITL(mo, lambda model: model.domain[A])
-    alg_c = ITL(mc, index_roi_constructor(A))
+    alg_c = ITL(mc, index_roi_constructor(A), conditioning=conditioning)
     agree, steps = _run_pair(alg_o, alg_c, table, T=12, teacher_forced=True, rtol_F=1e-6)
     assert steps == 12 and agree >= 10
 
@@ -282,13 +283,15 @@ def test_full_size_properties_n65536(cuda):
     w = (k / L) / L
     want = before - k[rows][:, None] * w[None, :]
     assert torch.equal(gp.cov[0, rows, :N], want)  # exact closed form, sampled rows
-    assert torch.equal(gp.cov[0, idx, :N], gp.cov[0, :, idx])  # still symmetric along the touched row
+    # symmetric up to rounding: k[a]*w[b] and k[b]*w[a] round differently, in the
+    # reference's Kxt.T @ Sigma_inv_Kxt (gaussian_distribution.py:36) just the same
+    torch.testing.assert_close(gp.cov[0, idx, :N], gp.cov[0, :, idx], rtol=1e-5, atol=1e-7)
     assert torch.equal(gp.var[0].float(), torch.diagonal(gp.cov[0, :, :N]))
     # scoring: VTL with a 4,096-point target set, rows variant == symmetric column variant
     A = torch.as_tensor(np.sort(np.random.default_rng(0).choice(N, 4096, replace=False)), device=cuda)
     F1 = gp.score_rows(_abi.RULE_VTL, A, 4096)
     F2 = gp.score_rows(_abi.RULE_VTL, A, 4096, sharded_cols=True)
-    torch.testing.assert_close(F1, F2, rtol=1e-9, atol=0)
+    torch.testing.assert_close(F1, F2, rtol=1e-6, atol=0)  # fp32 storage: cov is symmetric to rounding only
     gp.masked_argmax(F1.clone(), None, 1, None)
     r = gp.read_result()
     assert r.status == 0 and float(F1[r.idx]) == float(F1.max()) == r.val

@@ -50,6 +50,55 @@ gather_roi_S_kernel(const double* __restrict__ B, i64 ldb, const i64* __restrict
   S[j * lds + k] = v;
 }
 
+// Row-sharded variants: this GPU holds covariance rows [row0, row0 + n_loc).
+// B[j][x] = cov[A_j][row0 + x] is read through the symmetric entry
+// cov_loc[x][A_j] (a transposing gather staged in shared memory so that both
+// the scattered reads stay inside one row and the writes are coalesced);
+// S gets the rows j whose A_j this GPU owns (others zero: a sum over the
+// shards assembles S; the identity pad is contributed by the shard with row0 = 0).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_roi_cols_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, const i64* __restrict__ roi_idx,
+                       i64 m, double* __restrict__ B, i64 ldb, i64 ncols) {
+  __shared__ double tile[32][33];
+  const i64 x0 = (i64)blockIdx.x * 32, j0 = (i64)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const i64 j = j0 + tx;
+  const i64 a = j < m ? roi_idx[j] : -1;
+  for (int r = ty; r < 32; r += 8) {
+    const i64 x = x0 + r;
+    double v = 0.0;
+    if (a >= 0 && x < n_loc) v = (double)cov[x * ld + a];
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const i64 jj = j0 + r, x = x0 + tx;
+    if (x < ncols) B[jj * ldb + x] = tile[tx][r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_roi_S_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc,
+                         const i64* __restrict__ roi_idx, i64 m, i64 m_pad, double jitter,
+                         double* __restrict__ S, i64 lds) {
+  const i64 j = blockIdx.y;
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m_pad) return;
+  double v = 0.0;
+  if (j < m && k < m) {
+    const i64 r = roi_idx[j] - row0;
+    if (r >= 0 && r < n_loc) {
+      v = (double)cov[r * ld + roi_idx[k]];
+      if (j == k) v = v + jitter * jitter;
+    }
+  } else if (j == k && row0 == 0) {
+    v = 1.0;
+  }
+  S[j * lds + k] = v;
+}
+
 // --------------------------------------------------------------------------
 // DMMA GEMM core:  acc[BM x BN] += A[BM x K] * B[K x BN]
 //   A row-major (k contiguous).  B either [k][n] (NN) or [n][k] (NT).
@@ -380,6 +429,31 @@ int tal_gather_roi(const void* cov, long long ld, long long N, const long long* 
   dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
   gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
   TAL_LAUNCH_CHECK("tal_gather_roi/S");
+  return TAL_OK;
+}
+
+int tal_gather_roi_sharded(const void* cov, long long ld, long long row0, long long n_loc,
+                           const long long* roi_idx, long long m, long long m_pad, double jitter,
+                           double* S, long long lds, double* B, long long ldb, long long ncols,
+                           int dtype, void* stream) {
+  TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
+  TAL_ARG(lds >= m_pad && ldb >= ncols && ncols >= n_loc && m_pad <= 65535 && n_loc >= 0);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  cudaStream_t st = as_stream(stream);
+  dim3 gb((unsigned)((ncols + 31) / 32), (unsigned)(m_pad / 32));
+  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  if (dtype == TAL_F64) {
+    gather_roi_cols_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, n_loc, roi_idx, m, B, ldb, ncols);
+    TAL_LAUNCH_CHECK("tal_gather_roi_sharded/B");
+    gather_roi_S_rows_kernel<double><<<gs, 256, 0, st>>>((const double*)cov, ld, row0, n_loc, roi_idx, m,
+                                                        m_pad, jitter, S, lds);
+  } else {
+    gather_roi_cols_kernel<float><<<gb, 256, 0, st>>>((const float*)cov, ld, n_loc, roi_idx, m, B, ldb, ncols);
+    TAL_LAUNCH_CHECK("tal_gather_roi_sharded/B");
+    gather_roi_S_rows_kernel<float><<<gs, 256, 0, st>>>((const float*)cov, ld, row0, n_loc, roi_idx, m,
+                                                       m_pad, jitter, S, lds);
+  }
+  TAL_LAUNCH_CHECK("tal_gather_roi_sharded/S");
   return TAL_OK;
 }
 

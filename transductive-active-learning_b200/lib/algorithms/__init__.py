@@ -92,7 +92,9 @@ def fixed_roi_constructor(roi_description) -> ROIConstructor:
 
     def ctor(model: MarginalModel) -> ROI:
         if id(model) not in cache:  # the description and the domain never change
-            cache[id(model)] = ROI.from_mask(model, compute_roi_mask(model.domain, roi_description))
+            roi = ROI.from_mask(model, compute_roi_mask(model.domain, roi_description))
+            roi.fixed = True
+            cache[id(model)] = roi
         return cache[id(model)]
 
     return ctor
@@ -106,7 +108,7 @@ def index_roi_constructor(indices) -> ROIConstructor:
     def ctor(model: MarginalModel) -> ROI:
         if id(model) not in cache:
             idx = torch.as_tensor(indices, dtype=torch.int64).to(model.domain.device).contiguous()
-            cache[id(model)] = ROI(model, idx, idx.numel(), None)
+            cache[id(model)] = ROI(model, idx, idx.numel(), None, fixed=True)
         return cache[id(model)]
 
     return ctor

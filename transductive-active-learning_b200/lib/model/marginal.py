@@ -44,11 +44,12 @@ class ROI:
     reference's array on demand."""
 
     def __init__(self, model: "MarginalModel", idx: torch.Tensor, m: int,
-                 mask: Optional[torch.Tensor] = None):
+                 mask: Optional[torch.Tensor] = None, fixed: bool = False):
         self.model = model
         self.idx = idx  # int64 device tensor, first m entries valid (ascending)
         self.m = int(m)
         self.mask = mask
+        self.fixed = fixed  # the constructor returns this same object at every step
 
     @classmethod
     def from_mask(cls, model: "MarginalModel", mask: torch.Tensor) -> "ROI":

@@ -68,11 +68,15 @@ SIGNATURES = {
     "tal_pred_var_inv": (_i, [_p, _p, _ll, _p, _p]),
     "tal_score_rows_finish": (_i, [_i, _p, _p, _p, _p, _ll, _i, _p, _p]),
     "tal_gather_roi": (_i, [_p, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _i, _p]),
+    "tal_gather_roi_sharded": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _ll, _i, _p]),
     "tal_potrf_work_bytes": (_ll, [_ll]),
     "tal_potrf_lower": (_i, [_p, _ll, _ll, _p, _p]),
     "tal_trsm_lower": (_i, [_p, _ll, _ll, _p, _p, _ll, _ll, _p]),
     "tal_colsumsq_dense": (_i, [_p, _ll, _ll, _ll, _p, _i, _p, _p]),
     "tal_score_itl_directed": (_i, [_p, _p, _p, _ll, _i, _p, _p]),
+    "tal_cond_extract_col": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p]),
+    "tal_cond_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _ll, _p, _p, _i, _p]),
+    "tal_cond_coef_bytes": (_ll, [_ll]),
     "tal_argmax_scratch_bytes": (_ll, []),
     "tal_masked_argmax": (_i, [_p, _p, _p, _i, _i, _ll, _p, _ll, _ll, _p, _p, _p]),
     "tal_argmax_combine": (_i, [_p, _i, _p, _p]),

@@ -92,6 +92,7 @@ class DeviceGP:
         self._y_host = torch.zeros((q,), dtype=torch.float64).pin_memory()
         self._y_dev = torch.zeros((q,), **f64)
         self._ws = {}  # named scratch tensors, grown on demand
+        self._cond = None  # incremental conditioning state (score_itl_directed)
 
     # ------------------------------------------------------------------ util
     def _scratch(self, name: str, shape, dtype=torch.float64) -> torch.Tensor:
@@ -193,6 +194,8 @@ class DeviceGP:
         if allreduce is not None:
             allreduce(self.kbuf)
         self.step_vectors(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
+        if self._cond is not None and self._cond["valid"]:
+            self._cond_downdate(idx_dev, idx_host)
         self.rank1_update()
 
     def condition(self, i: int, obs_idx: torch.Tensor, y: torch.Tensor,
@@ -204,6 +207,8 @@ class DeviceGP:
         m_total = int(obs_idx.numel())
         if m_total == 0:  # :23-24 short-circuit
             return
+        if self._cond is not None:
+            self._cond["valid"] = False  # general-m update: re-condition from scratch next time
         obs_idx = obs_idx.to(device=self.device, dtype=torch.int64).contiguous()
         y = y.to(device=self.device, dtype=torch.float64).contiguous()
         if noise_std is not None:
@@ -318,18 +323,20 @@ class DeviceGP:
                 1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
         return F
 
-    def cond_var_sumsq(self, i: int, roi_idx: torch.Tensor, m: int,
-                       jitter: float = 1e-5) -> torch.Tensor:
+    def cond_var_sumsq(self, i: int, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
+                       V: Optional[torch.Tensor] = None,
+                       cs: Optional[torch.Tensor] = None) -> torch.Tensor:
         """cs[x] = || L^-1 cov_i[A, x] ||^2 with L = chol(cov_i[A, A] + jitter^2 I):
         the part of compute_posterior_covariance's diagonal that directed ITL
-        uses (itl.py:41-48).  One GPU (full rows)."""
+        uses (itl.py:41-48).  One GPU (full rows).  V / cs: optional persistent
+        buffers ([m_pad, ncols] / [ncols]) that receive L^-1 cov_i[A, :] and cs."""
         assert self.n_loc == self.N, "conditioning needs the full rows on this device"
         lib = self.lib
         m_pad = round_up(m, 128)
         ncols = round_up(self.N, 64)
         ldb = ncols
         S = self._scratch("cv_S", (m_pad, m_pad))
-        B = self._scratch("cv_B", (m_pad, ldb))
+        B = self._scratch("cv_B", (m_pad, ldb)) if V is None else V
         work = self._scratch("cv_work", (int(lib.tal_potrf_work_bytes(m_pad)) // 8,))
         _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m, m_pad,
                                       float(jitter), _ptr(S), m_pad, _ptr(B), ldb, self.dt,
@@ -340,19 +347,64 @@ class DeviceGP:
                                       _stream()), "tal_trsm_lower")
         n_split = int(max(1, min(64, m_pad // 64, -(-1184 // max(1, ncols // 512)))))
         part = self._scratch("cv_part", (n_split, ncols))
-        cs = self._scratch("cv_cs", (ncols,))
+        if cs is None:
+            cs = self._scratch("cv_cs", (ncols,))
         _abi.check(lib.tal_colsumsq_dense(_ptr(B), ldb, m_pad, ncols, _ptr(part), n_split,
                                           _ptr(cs), _stream()), "tal_colsumsq_dense")
         return cs[: self.N]
 
-    def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5) -> torch.Tensor:
+    def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
+                           incremental: bool = False, roi_key=None) -> torch.Tensor:
+        """sum_i 0.5 max(log((var_i + rho_i^2)/(var_i - cs_i + rho_i^2)), 0) (itl.py:50-58).
+        incremental: keep V_i = L^-1 cov_i[A, :] resident and let `observe`
+        downdate it (csrc/condinc.cu) as long as `roi_key` stays the same; the
+        full Cholesky + TRSM then only runs when the ROI changes."""
         F = torch.empty((self.N,), dtype=torch.float64, device=self.device)
+        st = self._cond
+        reuse = incremental and st is not None and st["key"] is roi_key and st["valid"]
+        if incremental and not reuse:
+            m_pad, ncols = round_up(m, 128), round_up(self.N, 64)
+            if st is None or st["V"].shape != (self.q, m_pad, ncols):
+                self._cond = st = None  # drop the old buffers before allocating
+                st = dict(V=torch.empty((self.q, m_pad, ncols), dtype=torch.float64, device=self.device),
+                          cs=torch.empty((self.q, ncols), dtype=torch.float64, device=self.device),
+                          pcol=torch.empty((m_pad,), dtype=torch.float64, device=self.device),
+                          coef=torch.empty((int(self.lib.tal_cond_coef_bytes(m_pad)) // 8,),
+                                           dtype=torch.float64, device=self.device))
+            st.update(key=roi_key, m_pad=m_pad, ncols=ncols, valid=False)
+            self._cond = st
         for i in range(self.q):
-            cs = self.cond_var_sumsq(i, roi_idx, m, jitter)
+            if reuse:
+                cs = st["cs"][i, : self.N]
+            elif incremental:
+                cs = self.cond_var_sumsq(i, roi_idx, m, jitter, V=st["V"][i], cs=st["cs"][i])
+            else:
+                cs = self.cond_var_sumsq(i, roi_idx, m, jitter)
             _abi.check(self.lib.tal_score_itl_directed(
                 _ptr(self.var[i]), _ptr(cs), _ptr(self.rho[i]), self.N, 1 if i > 0 else 0,
                 _ptr(F), _stream()), "tal_score_itl_directed")
+        if incremental:
+            st["valid"] = True
         return F
+
+    def _cond_downdate(self, idx_dev, idx_host, allreduce=None) -> None:
+        """After extract_row + step_vectors of an observation: V_i <- T^-1 (V_i - V_i[:, x] w^T)."""
+        st = self._cond
+        for i in range(self.q):
+            V = st["V"][i]
+            _abi.check(self.lib.tal_cond_extract_col(
+                _ptr(V), st["ncols"], st["m_pad"], 0, st["ncols"], _ptr(idx_dev), int(idx_host),
+                _ptr(st["pcol"]), _stream()), "tal_cond_extract_col")
+            if allreduce is not None:
+                allreduce(st["pcol"])
+            _abi.check(self.lib.tal_cond_update(
+                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.N, 0, _ptr(st["pcol"]),
+                _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]), _ptr(idx_dev),
+                int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]), self.dt, _stream()),
+                "tal_cond_update")
+
+    def drop_conditioning(self) -> None:
+        self._cond = None
 
     # ------------------------------------------------------------------ argmax
     def masked_argmax(self, F: torch.Tensor, safe: Optional[torch.Tensor], first_constraint: int,
