@@ -1,0 +1,110 @@
+"""The row-sharded path (talgp/dist.py) on ONE GPU: G host threads drive one
+shard each through the very code that runs under NCCL (ShardedGP /
+ShardedITLBench), with the two exchange steps emulated between the threads.
+The result must reproduce the single-GPU engine: covariance rows bit for bit,
+scores and selections within tolerance."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning):
+    from talgp.dist import ShardedITLBench, ThreadComm
+    shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
+    out = [None] * G
+    errs = []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(cuda)
+            b = ShardedITLBench(domain, A, table, w, G, rank, cuda, conditioning,
+                                comm=ThreadComm(shared, rank, G))
+            sel, Fs = [], []
+            for t in range(steps):
+                F = b.sg.score_itl_directed(b.roi, b.m, incremental=b.inc)
+                Fs.append(F.clone())
+                rec = b.sg.masked_argmax(F, 1, None)
+                sel.append(int(rec[0].item()))
+                b.sg.observe(rec[0:1], b.table, b.beta, True, w["N"])
+            out[rank] = (b, sel, Fs)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            shared["barrier"].abort()
+
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+    return out
+
+
+@pytest.mark.parametrize("conditioning", ["incremental", "recompute"])
+@pytest.mark.parametrize("G", [2, 3])
+def test_sharded_itl_matches_single_gpu(cuda, G, conditioning):
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import make_problem
+    from talgp import _abi
+    from talgp.engine import DeviceGP
+    w = dict(N=700, m=90, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=6)
+    domain, A, table = make_problem(w)
+    N, steps = w["N"], 8
+    # single-GPU engine
+    gp = DeviceGP(N, 1, device=cuda)
+    dom = torch.as_tensor(domain, device=cuda).contiguous()
+    gp.build_gram(0, _abi.KERNEL_MATERN52, 1.0, w["lengthscale"], dom)
+    gp.rho.fill_(w["rho"]); gp.init_bounds([1.0])
+    roi = torch.as_tensor(A, device=cuda)
+    tab = torch.as_tensor(table, device=cuda)
+    sel1, F1 = [], []
+    for t in range(steps):
+        F = gp.score_itl_directed(roi, len(A), incremental=(conditioning == "incremental"), roi_key=roi)
+        F1.append(F.clone())
+        rec = gp.masked_argmax(F, None, 1, None)
+        sel1.append(int(rec[0].item()))
+        gp.observe(rec[0:1].clone(), tab, [1.0], y_gather=True, y_stride=N)
+    out = _run_sharded(cuda, G, domain, A, table, w, steps, conditioning)
+    # every rank saw the same selections, equal to the single-GPU run
+    for b, sel, Fs in out:
+        assert sel == sel1
+    for t in range(steps):
+        Fcat = torch.cat([out[r][2][t] for r in range(G)])
+        torch.testing.assert_close(Fcat, F1[t], rtol=1e-7, atol=1e-10)
+    rows = torch.cat([out[r][0].gp.cov[0] for r in range(G)])
+    assert torch.equal(rows, gp.cov[0])  # the shards' rows ARE the single-GPU matrix
+    for r in range(G):
+        g = out[r][0].gp
+        assert torch.equal(g.mean, gp.mean) and torch.equal(g.var, gp.var)
+        assert torch.equal(g.l, gp.l) and torch.equal(g.u, gp.u)
+
+
+def test_sharded_vtl_columns_match_rows(cuda):
+    """VTL over a shard's own candidates through the symmetric column gather."""
+    from talgp import _abi
+    from talgp.dist import shard_rows
+    from talgp.engine import DeviceGP
+    import oracle as O
+    N, q = 500, 2
+    rng = np.random.default_rng(4)
+    domain = rng.random((N, 3))
+    covs = [O.Matern52(lengthscale=0.3).covariance(domain), O.Gaussian(lengthscale=0.2).covariance(domain)]
+    full = DeviceGP(N, q, device=cuda)
+    for i in range(q):
+        full.load_covariance(i, torch.as_tensor(covs[i]))
+    full.rho.fill_(0.1)
+    roi = torch.as_tensor(np.sort(rng.choice(N, 70, replace=False)), device=cuda)
+    F = full.score_rows(_abi.RULE_VTL, roi, 70)
+    parts = []
+    for r in range(3):
+        row0, n_loc = shard_rows(N, 3, r)
+        sh = DeviceGP(N, q, device=cuda, row0=row0, n_loc=n_loc)
+        for i in range(q):
+            sh.load_covariance(i, torch.as_tensor(covs[i]))
+        sh.rho.fill_(0.1)
+        parts.append(sh.score_rows(_abi.RULE_VTL, roi, 70, sharded_cols=True))
+    torch.testing.assert_close(torch.cat(parts), F, rtol=1e-10, atol=0)

@@ -88,9 +88,12 @@ cond_coeffs_kernel(const double* __restrict__ pcol, i64 m_pad, const T* __restri
 }
 
 // V <- T^-1 (V - V[:, x*] w^T), cs[x] = sum_j V'[j][x]^2.  One thread per pair of
-// columns; rows are read UNROLL at a time (independent 16-byte loads in flight).
+// columns walks down the m rows (the recurrence is sequential in j but its
+// loads are not): rows are read UNROLL at a time and the NEXT batch of loads is
+// issued before the current batch is processed and stored, so that
+// 2 * UNROLL * 16 bytes per thread are in flight (there are only N/2 threads).
 template <typename T, int UNROLL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 cond_update_kernel(double* __restrict__ V, i64 ldv, i64 m_pad, i64 ncols, i64 n_valid, i64 col0,
                    const CondCoef* __restrict__ coef, const double* __restrict__ pcol,
                    const T* __restrict__ wbuf, double* __restrict__ cs) {
@@ -102,10 +105,14 @@ cond_update_kernel(double* __restrict__ V, i64 ldv, i64 m_pad, i64 ncols, i64 n_
   double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
   double2* Vp = reinterpret_cast<double2*>(V + col);
   const i64 ldv2 = ldv / 2;
-  for (i64 j = 0; j < m_pad; j += UNROLL) {
-    double2 y[UNROLL];
+  double2 y[UNROLL], yn[UNROLL];
 #pragma unroll
-    for (int t = 0; t < UNROLL; ++t) y[t] = ld_stream(Vp + (j + t) * ldv2);
+  for (int t = 0; t < UNROLL; ++t) y[t] = ld_stream(Vp + (i64)t * ldv2);
+  for (i64 j = 0; j < m_pad; j += UNROLL) {
+    if (j + UNROLL < m_pad) {
+#pragma unroll
+      for (int t = 0; t < UNROLL; ++t) yn[t] = ld_stream(Vp + (j + UNROLL + t) * ldv2);
+    }
 #pragma unroll
     for (int t = 0; t < UNROLL; ++t) {
       const CondCoef c = coef[j + t];
@@ -118,6 +125,8 @@ cond_update_kernel(double* __restrict__ V, i64 ldv, i64 m_pad, i64 ncols, i64 n_
       q1 += z1 * z1;
       st_stream(Vp + (j + t) * ldv2, make_double2(z0, z1));
     }
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) y[t] = yn[t];
   }
   cs[col] = q0;
   cs[col + 1] = q1;
@@ -156,12 +165,12 @@ int tal_cond_update(double* V, long long ldv, long long m_pad, long long ncols, 
     cond_coeffs_kernel<float><<<1, 1024, 0, st>>>(pcol, m_pad, (const float*)kbuf_i, rho_i, idx_dev,
                                                   idx_host, coef);
   TAL_LAUNCH_CHECK("tal_cond_update/coeffs");
-  const unsigned grid = (unsigned)((ncols / 2 + 127) / 128);
+  const unsigned grid = (unsigned)((ncols / 2 + 63) / 64);
   if (dtype == TAL_F64)
-    cond_update_kernel<double, 8><<<grid, 128, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
+    cond_update_kernel<double, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
                                                         (const double*)wbuf_i, cs);
   else
-    cond_update_kernel<float, 8><<<grid, 128, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
+    cond_update_kernel<float, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
                                                        (const float*)wbuf_i, cs);
   TAL_LAUNCH_CHECK("tal_cond_update");
   return TAL_OK;

@@ -239,7 +239,7 @@ __device__ __forceinline__ void acc_store(double* __restrict__ D, i64 ldd,
     }
 }
 
-typedef GemmCfg<128, 64, 4, 2, 4> TrsmCfg;  // 256 threads, warp tile 32 x 32
+typedef GemmCfg<128, 64, 4, 2, 3> TrsmCfg;  // 256 threads, warp tile 32 x 32, 2 CTAs / SM
 
 // --------------------------------------------------------------------------
 // TRSM:  B <- L^-1 B.  One CTA per strip of BN columns; block row i:
@@ -275,49 +275,108 @@ trsm_lower_kernel(const double* __restrict__ L, i64 lds, int m, const double* __
 // Cholesky, right-looking, block size NB.
 // --------------------------------------------------------------------------
 // (1) factor the diagonal block in shared memory, write L_jj and inv(L_jj).
-__global__ void __launch_bounds__(256)
+//     512 threads = 4 lanes per row.  Left-looking (Crout): column c of the
+//     UNscaled factor U[r][c] = L[r][c] * L[c][c] is a dot product over the
+//     finished columns, U[r][c] = A[r][c] - sum_{k<c} U[r][k] U[c][k] g[k] with
+//     g[k] = 1 / U[k][k]; dot products carry no stores, so the loads pipeline
+//     (a right-looking update is latency-bound on shared memory here), the 4
+//     lanes of a row are reduced by shuffles, and one barrier per column
+//     suffices.  The inverse is then formed in place row by row:
+//     X[r][c] = -(sum_{c<=k<r} L[r][k] X[k][c]) / L[r][r] only needs row r of L.
+//     Row pitch 132 doubles keeps the 64-bit accesses of both phases conflict-free.
+constexpr int DIAG_P = NB + 4;
+constexpr int DIAG_THREADS = 4 * NB;
+__global__ void __launch_bounds__(DIAG_THREADS)
 potrf_diag_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ Linv_all) {
-  extern __shared__ __align__(16) double sm[];  // [NB][NB+1]
-  constexpr int P = NB + 1;
+  extern __shared__ __align__(16) double sm[];  // [NB][DIAG_P] + g[NB]
+  constexpr int P = DIAG_P;
+  double* g = sm + NB * P;
   double* D = S + (i64)j * NB * lds + (i64)j * NB;
   double* Linv = Linv_all + (i64)j * NB * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    sm[r * P + c] = (c <= r) ? D[(i64)r * lds + c] : 0.0;
+  const int r = threadIdx.x >> 2, h = threadIdx.x & 3;
+  for (int e = threadIdx.x; e < NB * NB; e += DIAG_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    sm[rr * P + cc] = (cc <= rr) ? D[(i64)rr * lds + cc] : 0.0;
   }
   __syncthreads();
   for (int c = 0; c < NB; ++c) {
-    if (threadIdx.x == 0) sm[c * P + c] = sqrt(sm[c * P + c]);  // NaN if not positive definite
-    __syncthreads();
-    const double d = sm[c * P + c];
-    for (int r = c + 1 + threadIdx.x; r < NB; r += blockDim.x) sm[r * P + c] /= d;
-    __syncthreads();
-    // trailing update of the lower triangle: rows r > c, cols c < k <= r
-    const int n = NB - c - 1;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-      const int r = c + 1 + e / n, k = c + 1 + e % n;
-      if (k <= r) sm[r * P + k] -= sm[r * P + c] * sm[k * P + c];
-    }
-    __syncthreads();
-  }
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    if (c <= r) D[(i64)r * lds + c] = sm[r * P + c];
-  }
-  // inverse by forward substitution, one column per thread (columns >= NB idle)
-  const int c = threadIdx.x;
-  if (c < NB) {
-    for (int r = 0; r < NB; ++r) {
-      double x;
-      if (r < c) {
-        x = 0.0;
-      } else {
-        double s = (r == c) ? 1.0 : 0.0;
-        for (int k = c; k < r; ++k) s -= sm[r * P + k] * Linv[k * NB + c];
-        x = s / sm[r * P + r];
+    double acc = 0.0;
+    if (r >= c) {
+      const double* ur = sm + r * P;
+      const double* uc = sm + c * P;
+      // four independent partial sums: the fp64 FMA chain is the critical path
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = h;
+      for (; k + 12 < c; k += 16) {
+        a0 += ur[k] * (uc[k] * g[k]);
+        a1 += ur[k + 4] * (uc[k + 4] * g[k + 4]);
+        a2 += ur[k + 8] * (uc[k + 8] * g[k + 8]);
+        a3 += ur[k + 12] * (uc[k + 12] * g[k + 12]);
       }
-      Linv[r * NB + c] = x;
+      for (; k < c; k += 4) a0 += ur[k] * (uc[k] * g[k]);
+      acc = (a0 + a1) + (a2 + a3);
     }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (r >= c && h == 0) {
+      const double u = sm[r * P + c] - acc;
+      sm[r * P + c] = u;
+      if (r == c) g[c] = 1.0 / u;
+    }
+    __syncthreads();
+  }
+  // scale to L: L[r][c] = U[r][c] / sqrt(U[c][c]); NaN when not positive definite
+  for (int e = threadIdx.x; e < NB * NB; e += DIAG_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    if (cc <= rr) {
+      const double d = sqrt(sm[cc * P + cc]);
+      const double v = (cc == rr) ? d : sm[rr * P + cc] / d;
+      D[(i64)rr * lds + cc] = v;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += DIAG_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    if (cc < rr) sm[rr * P + cc] *= sqrt(g[cc]);  // 1/sqrt(U[cc][cc])
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) {
+    const int t = threadIdx.x;
+    const double d = sqrt(sm[t * P + t]);
+    sm[t * P + t] = d;
+    g[t] = 1.0 / d;  // reciprocal diagonal, off the serial path of the inverse
+  }
+  __syncthreads();
+  // in-place inverse, row by row; here thread (c, h): column c, lane h
+  const int c = r;
+  for (int rr = 0; rr < NB; ++rr) {
+    const double* lr = sm + rr * P;
+    double acc = 0.0;
+    if (c < rr) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = c + h;
+      for (; k + 12 < rr; k += 16) {
+        a0 += lr[k] * sm[k * P + c];
+        a1 += lr[k + 4] * sm[(k + 4) * P + c];
+        a2 += lr[k + 8] * sm[(k + 8) * P + c];
+        a3 += lr[k + 12] * sm[(k + 12) * P + c];
+      }
+      for (; k < rr; k += 4) a0 += lr[k] * sm[k * P + c];
+      acc = (a0 + a1) + (a2 + a3);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    const double il = g[rr];
+    __syncthreads();  // row rr of L has been read by everyone
+    if (h == 0) {
+      if (c < rr) sm[rr * P + c] = -acc * il;
+      else if (c == rr) sm[rr * P + rr] = il;
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NB * NB; e += DIAG_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    Linv[e] = (cc <= rr) ? sm[rr * P + cc] : 0.0;
   }
 }
 
@@ -465,7 +524,7 @@ int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void*
   TAL_ARG(S && work && m_pad >= NB && m_pad % NB == 0 && lds >= m_pad && lds % 2 == 0);
   cudaStream_t st = as_stream(stream);
   static bool a0 = false, a1 = false, a2 = false;
-  const int diag_smem = NB * (NB + 1) * (int)sizeof(double);
+  const int diag_smem = (NB * DIAG_P + NB) * (int)sizeof(double);
   if (!a0) {
     TAL_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   diag_smem));
@@ -476,7 +535,7 @@ int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void*
   const int nblk = (int)(m_pad / NB);
   double* Linv = (double*)work;
   for (int j = 0; j < nblk; ++j) {
-    potrf_diag_kernel<<<1, 256, diag_smem, st>>>(S, lds, j, Linv);
+    potrf_diag_kernel<<<1, DIAG_THREADS, diag_smem, st>>>(S, lds, j, Linv);
     TAL_LAUNCH_CHECK("tal_potrf_lower/diag");
     const int rem = nblk - j - 1;
     if (rem > 0) {

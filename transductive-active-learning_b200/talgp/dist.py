@@ -76,16 +76,60 @@ def status_of(flags: int) -> int:
     return 0
 
 
+class NcclComm:
+    """The two exchange steps over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def sum_(self, buf: torch.Tensor) -> torch.Tensor:
+        return sum_broadcast(buf, self.group)
+
+    def gather_records(self, rec: torch.Tensor, out: torch.Tensor) -> None:
+        dist.all_gather_into_tensor(out.view(-1), rec, group=self.group)
+
+
+class ThreadComm:
+    """The same exchange steps between `world` Python threads that drive one
+    shard each on ONE GPU (all on the same stream, so kernels serialise in issue
+    order and never wait on one another).  Used to test the sharded path on a
+    single GPU: the ShardedGP code is the one that runs under NCCL."""
+
+    def __init__(self, shared: dict, rank: int, world: int):
+        self.shared, self.rank, self.world = shared, rank, world
+
+    def sum_(self, buf: torch.Tensor) -> torch.Tensor:
+        sh = self.shared
+        sh["slots"][self.rank] = buf
+        sh["barrier"].wait()
+        tot = sh["slots"][0].clone()
+        for r in range(1, self.world):
+            tot += sh["slots"][r]
+        sh["barrier"].wait()  # every thread has issued its reads
+        buf.copy_(tot)
+        sh["barrier"].wait()
+        return buf
+
+    def gather_records(self, rec: torch.Tensor, out: torch.Tensor) -> None:
+        sh = self.shared
+        sh["slots"][self.rank] = rec
+        sh["barrier"].wait()
+        for r in range(self.world):
+            out[r].copy_(sh["slots"][r])
+        sh["barrier"].wait()
+
+
 # ------------------------------------------------------------------ device side
 class ShardedGP:
     """DeviceGP restricted to this rank's row block + the two exchange steps."""
 
-    def __init__(self, N: int, q: int, dtype=torch.float64, device=None, group=None,
+    def __init__(self, N: int, q: int, dtype=torch.float64, device=None, comm=None,
                  rank1_variant: int = 0):
         from .engine import DeviceGP
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.group = group
+        self.comm = comm if comm is not None else NcclComm()
+        self.world, self.rank = self.comm.world, self.comm.rank
         self.row0, self.n_loc = shard_rows(N, self.world, self.rank)
         self.gp = DeviceGP(N, q, dtype=dtype, device=device, row0=self.row0, n_loc=self.n_loc,
                            rank1_variant=rank1_variant)
@@ -101,7 +145,7 @@ class ShardedGP:
         gp = self.gp
         gp.var[i].zero_()
         gp.build_gram(i, kind, variance, lengthscale, domain)
-        sum_broadcast(gp.var[i], self.group)  # each rank contributed its own diagonal block
+        self.comm.sum_(gp.var[i])  # each rank contributed its own diagonal block
 
     # -- arg-max ----------------------------------------------------------------
     def masked_argmax(self, F_loc: torch.Tensor, first_constraint: int,
@@ -116,7 +160,7 @@ class ShardedGP:
                                l_offset=self.row0)
         if self.world == 1:
             return rec
-        dist.all_gather_into_tensor(self._recs.view(-1), rec, group=self.group)
+        self.comm.gather_records(rec, self._recs)
         _abi.check(gp.lib.tal_argmax_combine(_ptr(self._recs), self.world, _ptr(self._combined),
                                              _stream()), "tal_argmax_combine")
         return self._combined
@@ -126,7 +170,7 @@ class ShardedGP:
                 y_gather: bool, y_stride: int) -> None:
         gp = self.gp
         gp.extract_row(idx_dev)
-        sum_broadcast(gp.kbuf, self.group)
+        self.comm.sum_(gp.kbuf)
         gp.step_vectors(idx_dev, 0, y_dev, y_stride, y_gather, beta)
         if self._cond is not None:
             self._cond_downdate(idx_dev)
@@ -160,7 +204,7 @@ class ShardedGP:
                     _ptr(gp.cov[i]), gp.ld, self.row0, self.n_loc, _ptr(roi_idx), m, m_pad,
                     float(jitter), _ptr(S), m_pad, _ptr(V), ncols, ncols, gp.dt, _stream()),
                     "tal_gather_roi_sharded")
-                sum_broadcast(S, self.group)  # Sigma_AA assembled from the owners' rows
+                self.comm.sum_(S)  # Sigma_AA assembled from the owners' rows
                 _abi.check(lib.tal_potrf_lower(_ptr(S), m_pad, m_pad, _ptr(work), _stream()),
                            "tal_potrf_lower")  # replicated: identical on every rank
                 _abi.check(lib.tal_trsm_lower(_ptr(S), m_pad, m_pad, _ptr(work), _ptr(V), ncols,
@@ -184,7 +228,7 @@ class ShardedGP:
             _abi.check(gp.lib.tal_cond_extract_col(
                 _ptr(V), st["ncols"], st["m_pad"], self.row0, self.n_loc, _ptr(idx_dev), 0,
                 _ptr(st["pcol"]), _stream()), "tal_cond_extract_col")
-            sum_broadcast(st["pcol"], self.group)
+            self.comm.sum_(st["pcol"])
             _abi.check(gp.lib.tal_cond_update(
                 _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_loc, self.row0,
                 _ptr(st["pcol"]), _ptr(gp.kbuf[i]), _ptr(gp.wbuf[i]), _ptr(gp.rho[i]),
@@ -199,11 +243,11 @@ class ShardedGP:
 class ShardedITLBench:
     """BASELINE config 3 row-sharded over the ranks: what bench.py times at --gpus > 1."""
 
-    def __init__(self, domain, A, table, w, world, rank, dev, conditioning="incremental"):
+    def __init__(self, domain, A, table, w, world, rank, dev, conditioning="incremental", comm=None):
         from . import _abi
         self.w = w
         N = w["N"]
-        self.sg = ShardedGP(N, 1, dtype=torch.float64, device=dev)
+        self.sg = ShardedGP(N, 1, dtype=torch.float64, device=dev, comm=comm)
         self.gp = self.sg.gp
         dom = torch.as_tensor(domain, device=dev).contiguous()
         self.sg.build_gram(0, _abi.KERNEL_MATERN52, 1.0, w["lengthscale"], dom)
@@ -228,7 +272,7 @@ class ShardedITLBench:
         idx_dev = rec[0:1]
         gp = self.gp
         gp.extract_row(idx_dev)
-        sum_broadcast(gp.kbuf)
+        self.sg.comm.sum_(gp.kbuf)
         gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta)
         if self.sg._cond is not None:
             self.sg._cond_downdate(idx_dev)
