@@ -131,6 +131,23 @@ def bench_condvar(N, m):
     emit(kernel="colsumsq_dense", m=m, N=N, ms=med, GBs=m * N * 8 / med / 1e6)
 
 
+def bench_condinc(N, m):
+    lib = _abi.load()
+    dev = torch.device("cuda")
+    V = torch.randn((m, N), dtype=torch.float64, device=dev) * 0.01
+    pcol = V[:, 777].clone()
+    kbuf = torch.ones((N,), dtype=torch.float64, device=dev)
+    wbuf = torch.randn((N,), dtype=torch.float64, device=dev) * 0.1
+    rho = torch.full((N,), 0.1, dtype=torch.float64, device=dev)
+    coef = torch.empty((int(lib.tal_cond_coef_bytes(m)) // 8,), dtype=torch.float64, device=dev)
+    cs = torch.empty((N,), dtype=torch.float64, device=dev)
+    med, mn = time_ms(lambda: _abi.check(lib.tal_cond_update(
+        _ptr(V), N, m, N, N, 0, _ptr(pcol), _ptr(kbuf), _ptr(wbuf), _ptr(rho), None, 777, _ptr(coef),
+        _ptr(cs), _abi.F64, _stream())), warm=2, reps=10)
+    emit(kernel="cond_update(+coeffs)", m=m, N=N, ms=med, ms_min=mn, GBs=2 * m * N * 8 / med / 1e6,
+         frac_of_measured=2 * m * N * 8 / med / 1e6 / PEAK)
+
+
 def bench_probe():
     lib = _abi.load()
     out = torch.zeros((1,), dtype=torch.float64, device="cuda")
@@ -174,6 +191,9 @@ if __name__ == "__main__":
         torch.cuda.empty_cache()
     if "condvar" in what:
         bench_condvar(N, m)
+        torch.cuda.empty_cache()
+    if "condinc" in what:
+        bench_condinc(N, m)
         torch.cuda.empty_cache()
     if "gram" in what:
         bench_gram(N)
