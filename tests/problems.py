@@ -82,7 +82,7 @@ def build_oracle(p):
     return model, alg, O.TableFunction(p["domain"], p["table"])
 
 
-def build_cuda(p, **alg_kw):
+def build_cuda(p, comm=None, **alg_kw):
     from lib.algorithms import index_roi_constructor, pe_roi_constructor, pm_roi_constructor
     from lib.algorithms.itl import ITL
     from lib.algorithms.vtl import VTL
@@ -95,7 +95,7 @@ def build_cuda(p, **alg_kw):
     q = len(p["kernels"])
     ks = [getattr(stationary, k)(variance=v, lengthscale=l) for k, v, l in p["kernels"]]
     noise = HomoscedasticNoise(q, np.asarray(p["rho"]))
-    distrs = prior_distr(noise, p["domain"], p["X0"], p["y0"], ks, [ZeroMean()] * q)
+    distrs = prior_distr(noise, p["domain"], p["X0"], p["y0"], ks, [ZeroMean()] * q, comm=comm)
     model = MarginalModel(0, p["domain"], distrs, beta=np.asarray(p["beta"], float), noise_rate=noise,
                           use_objective_as_constraint=p["fc_obj"])
     if isinstance(p["roi"], str):

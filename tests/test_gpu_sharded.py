@@ -25,11 +25,11 @@ def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning):
                                 comm=ThreadComm(shared, rank, G))
             sel, Fs = [], []
             for t in range(steps):
-                F = b.sg.score_itl_directed(b.roi, b.m, incremental=b.inc)
+                F = b.score()
                 Fs.append(F.clone())
-                rec = b.sg.masked_argmax(F, 1, None)
+                rec = b.gp.argmax_candidates(F, None, 1, None)
                 sel.append(int(rec[0].item()))
-                b.sg.observe(rec[0:1], b.table, b.beta, True, w["N"])
+                b.gp.observe(rec[0:1], b.table, b.beta, y_gather=True, y_stride=w["N"])
             out[rank] = (b, sel, Fs)
         except Exception as e:  # pragma: no cover
             errs.append(e)
@@ -108,3 +108,51 @@ def test_sharded_vtl_columns_match_rows(cuda):
         sh.rho.fill_(0.1)
         parts.append(sh.score_rows(_abi.RULE_VTL, roi, 70, sharded_cols=True))
     torch.testing.assert_close(torch.cat(parts), F, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
+def test_drop_in_api_row_sharded(cuda, name):
+    """The `lib.*` classes over a row-sharded model (3 ranks emulated by threads):
+    same selections, scores and posterior as the single-GPU model."""
+    import problems
+    from talgp.dist import ThreadComm
+    p = problems.ALL[name]()
+    T = min(p["T"], 8)
+    m1, a1, f1 = problems.build_cuda(p)
+    ref = []
+    for t in range(T):
+        r = a1.step(f1)
+        ref.append((m1.last_argmax.idx, r["F"].clone()))
+    G = 3
+    shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
+    out, errs = [None] * G, []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(cuda)
+            m, a, f = problems.build_cuda(p, comm=ThreadComm(shared, rank, G))
+            got = []
+            for t in range(T):
+                r = a.step(f)
+                got.append((m.last_argmax.idx, r["F"].clone()))
+            out[rank] = (m, got)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            shared["barrier"].abort()
+
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+    for rank in range(G):
+        m, got = out[rank]
+        for (i1, F1), (i2, F2) in zip(ref, got):
+            assert i1 == i2
+            fin = torch.isfinite(F1)
+            torch.testing.assert_close(F2[fin], F1[fin], rtol=1e-7, atol=1e-10)
+            assert torch.equal(torch.isneginf(F1), torch.isneginf(F2))
+        torch.testing.assert_close(m.means, m1.means, rtol=1e-10, atol=1e-13)
+        torch.testing.assert_close(m.variances, m1.variances, rtol=1e-10, atol=1e-13)
+        row0, n_loc = m.row_range
+        torch.testing.assert_close(m.covariances, m1.covariances[:, row0:row0 + n_loc], rtol=1e-10, atol=1e-13)

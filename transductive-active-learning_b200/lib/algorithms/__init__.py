@@ -57,8 +57,9 @@ class DiscreteGreedyAlgorithm(GreedyAlgorithm):
         return self._sample_mask
 
     def _step(self, f: Function, update_model: bool = True):
-        F = self.F()
+        F = self.F()  # row-sharded model: this rank's candidates only
         idx = self.model._argmax_index(F, self.sample_mask())  # masks F in place (:80-81)
+        F = self.model._gp.gather_candidates(F)
         X = self.model.domain[idx: idx + 1]
         y = f.observe(X)
         if update_model:

@@ -28,7 +28,9 @@ class ITL(DirectedDiscreteGreedyAlgorithm):
 
 def _undirected(model: MarginalModel) -> torch.Tensor:
     """:28-30 — sum_i log(1 + var_i / rho_i^2)."""
-    return model._gp.score_itl_undirected()
+    gp = model._gp
+    F = gp.score_itl_undirected()
+    return F[gp.row0: gp.row0 + gp.n_loc] if gp.sharded else F
 
 
 def _directed(model: MarginalModel, roi, incremental: bool = False) -> torch.Tensor:

@@ -149,8 +149,14 @@ class MarginalModel(Model):
 
     @property
     def covariances(self) -> torch.Tensor:
-        """[q, n, n] view of the HBM-resident covariances."""
+        """[q, n, n] view of the HBM-resident covariances (row-sharded model:
+        this rank's rows [q, n_loc, n], see `row_range`)."""
         return self._gp.cov[:, :, : self.n]
+
+    @property
+    def row_range(self):
+        """(row0, n_loc): the covariance rows / candidates this rank holds."""
+        return self._gp.row0, self._gp.n_loc
 
     @property
     def variances(self) -> torch.Tensor:
@@ -167,6 +173,8 @@ class MarginalModel(Model):
         MM-ITL rules use the streaming row-reduce kernels instead)."""
         if A is None:
             A = X
+        if self._gp.sharded:
+            raise NotImplementedError("sqd_correlation needs full covariance rows (row-sharded model)")
         X_idx = self.get_indices(X)
         A_idx = self.get_indices(A)
         cov = self.covariances[:, X_idx][:, :, A_idx].to(torch.float64)  # [q, n, m]
@@ -261,8 +269,10 @@ class MarginalModel(Model):
         safe = None
         if type(self).operating_safe_set is not MarginalModel.operating_safe_set:
             safe = self.operating_safe_set.view(torch.uint8)
-        self._gp.masked_argmax(F, safe, self.first_constraint, sample_mask)
-        res = self._gp.read_result()
+        gp = self._gp
+        if gp.sharded and F.numel() == self.n:  # a full-length objective: this rank's candidates
+            F = F[gp.row0: gp.row0 + gp.n_loc]
+        res = gp.read_result(gp.argmax_candidates(F, safe, self.first_constraint, sample_mask))
         self.last_argmax = res
         if res.status != _abi.ARGMAX_OK:
             raise Exception(_MESSAGES[res.status])

@@ -59,8 +59,15 @@ def nearest_index(domain: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
 class DeviceGP:
     def __init__(self, N: int, q: int, dtype: torch.dtype = torch.float64,
                  device: Optional[torch.device] = None, row0: int = 0,
-                 n_loc: Optional[int] = None, rank1_variant: int = 0):
+                 n_loc: Optional[int] = None, rank1_variant: int = 0, comm=None):
+        """comm: None (one GPU) or a communicator of talgp.dist (NcclComm /
+        ThreadComm): the covariance is then row-sharded over comm.world ranks and
+        this object holds rank comm.rank's block."""
         _abi.require_device()
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        if self.comm is not None:
+            from .dist import shard_rows
+            row0, n_loc = shard_rows(int(N), comm.world, comm.rank)
         self.lib = _abi.load()
         if q < 1 or q > _abi.TAL_MAX_Q:
             raise ValueError(f"q must be in [1, {_abi.TAL_MAX_Q}]")
@@ -93,6 +100,30 @@ class DeviceGP:
         self._y_dev = torch.zeros((q,), **f64)
         self._ws = {}  # named scratch tensors, grown on demand
         self._cond = None  # incremental conditioning state (score_itl_directed)
+        if self.comm is not None:
+            self._recs = torch.zeros((self.comm.world, 4), dtype=torch.int64, device=dev)
+            self._combined = torch.zeros((4,), dtype=torch.int64, device=dev)
+
+    @property
+    def sharded(self) -> bool:
+        return self.comm is not None
+
+    def _sum(self, buf: torch.Tensor) -> None:
+        """Complete a buffer that only its owner filled (sum = broadcast)."""
+        if self.comm is not None:
+            self.comm.sum_(buf)
+
+    def gather_candidates(self, F_loc: torch.Tensor) -> torch.Tensor:
+        """[n_loc] per-shard candidate vector -> [N] on every rank."""
+        if self.comm is None:
+            return F_loc
+        from .dist import shard_rows
+        per = shard_rows(self.N, self.comm.world, 0)[1]
+        pad = torch.zeros((per,), dtype=F_loc.dtype, device=self.device)
+        pad[: self.n_loc] = F_loc
+        out = torch.empty((self.comm.world * per,), dtype=F_loc.dtype, device=self.device)
+        self.comm.all_gather_(pad, out)
+        return out[: self.N]
 
     # ------------------------------------------------------------------ util
     def _scratch(self, name: str, shape, dtype=torch.float64) -> torch.Tensor:
@@ -133,8 +164,10 @@ class DeviceGP:
             self.var[i].copy_(torch.diagonal(self.cov[i, :, : self.N]).to(torch.float64))
         else:
             sl = slice(self.row0, self.row0 + self.n_loc)
+            self.var[i].zero_()
             self.var[i, sl].copy_(
                 torch.diagonal(self.cov[i, :, self.row0:self.row0 + self.n_loc]).to(torch.float64))
+            self._sum(self.var[i])  # every shard contributed its own diagonal block
 
     def load_covariance(self, i: int, cov) -> None:
         """Upload a full N x N covariance (host or device) into shard i."""
@@ -193,6 +226,8 @@ class DeviceGP:
         self.extract_row(idx_dev, idx_host)
         if allreduce is not None:
             allreduce(self.kbuf)
+        else:
+            self._sum(self.kbuf)
         self.step_vectors(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
         if self._cond is not None and self._cond["valid"]:
             self._cond_downdate(idx_dev, idx_host)
@@ -225,6 +260,8 @@ class DeviceGP:
                 ldb, self.dt, _stream()), "tal_gather_rows")
             if allreduce is not None:
                 allreduce(B)
+            else:
+                self._sum(B)
             _abi.check(self.lib.tal_small_posterior_weights(
                 _ptr(B), ldb, self.N, _ptr(oi), m,
                 _ptr(noise_std[s:e]) if noise_std is not None else None, float(jitter),
@@ -280,6 +317,7 @@ class DeviceGP:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
         lib = self.lib
         N = self.N
+        sharded_cols = sharded_cols or self.sharded
         n_out = self.n_loc if sharded_cols else N
         off = self.row0 if sharded_cols else 0
         F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
@@ -323,24 +361,34 @@ class DeviceGP:
                 1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
         return F
 
+    def _cond_dims(self, m: int):
+        return round_up(m, 128), round_up(max(self.n_loc, 1), 64)
+
     def cond_var_sumsq(self, i: int, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
                        V: Optional[torch.Tensor] = None,
                        cs: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cs[x] = || L^-1 cov_i[A, x] ||^2 with L = chol(cov_i[A, A] + jitter^2 I):
-        the part of compute_posterior_covariance's diagonal that directed ITL
-        uses (itl.py:41-48).  One GPU (full rows).  V / cs: optional persistent
-        buffers ([m_pad, ncols] / [ncols]) that receive L^-1 cov_i[A, :] and cs."""
-        assert self.n_loc == self.N, "conditioning needs the full rows on this device"
+        """cs[x] = || L^-1 cov_i[A, x] ||^2 with L = chol(cov_i[A, A] + jitter^2 I) for
+        this shard's candidates x: the part of compute_posterior_covariance's
+        diagonal that directed ITL uses (itl.py:41-48).  V / cs: optional
+        persistent buffers ([m_pad, ncols] / [ncols]) that receive L^-1 cov_i[A, :]
+        and cs.  Row-sharded: cov[A, x] is read as the symmetric cov[x, A], Sigma_AA
+        is assembled from the owners' rows by a sum, its Cholesky is replicated."""
         lib = self.lib
-        m_pad = round_up(m, 128)
-        ncols = round_up(self.N, 64)
+        m_pad, ncols = self._cond_dims(m)
         ldb = ncols
         S = self._scratch("cv_S", (m_pad, m_pad))
         B = self._scratch("cv_B", (m_pad, ldb)) if V is None else V
         work = self._scratch("cv_work", (int(lib.tal_potrf_work_bytes(m_pad)) // 8,))
-        _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m, m_pad,
-                                      float(jitter), _ptr(S), m_pad, _ptr(B), ldb, self.dt,
-                                      _stream()), "tal_gather_roi")
+        if self.comm is None:
+            _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m,
+                                          m_pad, float(jitter), _ptr(S), m_pad, _ptr(B), ldb,
+                                          self.dt, _stream()), "tal_gather_roi")
+        else:
+            _abi.check(lib.tal_gather_roi_sharded(
+                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, _ptr(roi_idx), m, m_pad,
+                float(jitter), _ptr(S), m_pad, _ptr(B), ldb, ncols, self.dt, _stream()),
+                "tal_gather_roi_sharded")
+            self._sum(S)
         _abi.check(lib.tal_potrf_lower(_ptr(S), m_pad, m_pad, _ptr(work), _stream()),
                    "tal_potrf_lower")
         _abi.check(lib.tal_trsm_lower(_ptr(S), m_pad, m_pad, _ptr(work), _ptr(B), ldb, ncols,
@@ -351,19 +399,21 @@ class DeviceGP:
             cs = self._scratch("cv_cs", (ncols,))
         _abi.check(lib.tal_colsumsq_dense(_ptr(B), ldb, m_pad, ncols, _ptr(part), n_split,
                                           _ptr(cs), _stream()), "tal_colsumsq_dense")
-        return cs[: self.N]
+        return cs[: self.n_loc]
 
     def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
                            incremental: bool = False, roi_key=None) -> torch.Tensor:
-        """sum_i 0.5 max(log((var_i + rho_i^2)/(var_i - cs_i + rho_i^2)), 0) (itl.py:50-58).
+        """sum_i 0.5 max(log((var_i + rho_i^2)/(var_i - cs_i + rho_i^2)), 0) (itl.py:50-58)
+        over this shard's candidates ([N] on one GPU, [n_loc] when row-sharded).
         incremental: keep V_i = L^-1 cov_i[A, :] resident and let `observe`
         downdate it (csrc/condinc.cu) as long as `roi_key` stays the same; the
         full Cholesky + TRSM then only runs when the ROI changes."""
-        F = torch.empty((self.N,), dtype=torch.float64, device=self.device)
+        n_out, off = self.n_loc, self.row0
+        F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
         st = self._cond
         reuse = incremental and st is not None and st["key"] is roi_key and st["valid"]
         if incremental and not reuse:
-            m_pad, ncols = round_up(m, 128), round_up(self.N, 64)
+            m_pad, ncols = self._cond_dims(m)
             if st is None or st["V"].shape != (self.q, m_pad, ncols):
                 self._cond = st = None  # drop the old buffers before allocating
                 st = dict(V=torch.empty((self.q, m_pad, ncols), dtype=torch.float64, device=self.device),
@@ -373,16 +423,18 @@ class DeviceGP:
                                            dtype=torch.float64, device=self.device))
             st.update(key=roi_key, m_pad=m_pad, ncols=ncols, valid=False)
             self._cond = st
+        if not incremental and st is not None:
+            st["valid"] = False
         for i in range(self.q):
             if reuse:
-                cs = st["cs"][i, : self.N]
+                cs = st["cs"][i, :n_out]
             elif incremental:
                 cs = self.cond_var_sumsq(i, roi_idx, m, jitter, V=st["V"][i], cs=st["cs"][i])
             else:
                 cs = self.cond_var_sumsq(i, roi_idx, m, jitter)
             _abi.check(self.lib.tal_score_itl_directed(
-                _ptr(self.var[i]), _ptr(cs), _ptr(self.rho[i]), self.N, 1 if i > 0 else 0,
-                _ptr(F), _stream()), "tal_score_itl_directed")
+                _ptr(self.var[i, off:]), _ptr(cs), _ptr(self.rho[i, off:]), n_out,
+                1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_itl_directed")
         if incremental:
             st["valid"] = True
         return F
@@ -393,15 +445,14 @@ class DeviceGP:
         for i in range(self.q):
             V = st["V"][i]
             _abi.check(self.lib.tal_cond_extract_col(
-                _ptr(V), st["ncols"], st["m_pad"], 0, st["ncols"], _ptr(idx_dev), int(idx_host),
-                _ptr(st["pcol"]), _stream()), "tal_cond_extract_col")
-            if allreduce is not None:
-                allreduce(st["pcol"])
+                _ptr(V), st["ncols"], st["m_pad"], self.row0, self.n_loc, _ptr(idx_dev),
+                int(idx_host), _ptr(st["pcol"]), _stream()), "tal_cond_extract_col")
+            self._sum(st["pcol"])
             _abi.check(self.lib.tal_cond_update(
-                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.N, 0, _ptr(st["pcol"]),
-                _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]), _ptr(idx_dev),
-                int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]), self.dt, _stream()),
-                "tal_cond_update")
+                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_loc, self.row0,
+                _ptr(st["pcol"]), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
+                _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]), self.dt,
+                _stream()), "tal_cond_update")
 
     def drop_conditioning(self) -> None:
         self._cond = None
@@ -418,6 +469,23 @@ class DeviceGP:
             int(first_constraint), self.N, _ptr(sample), n, int(idx_offset),
             _ptr(self._argmax_scratch), _ptr(self._result), _stream()), "tal_masked_argmax")
         return self._result
+
+    def argmax_candidates(self, F_loc: torch.Tensor, safe: Optional[torch.Tensor],
+                          first_constraint: int, sample: Optional[torch.Tensor]) -> torch.Tensor:
+        """Masked arg-max over ALL candidates given this shard's scores: local
+        reduce, all-gather of the 32-byte records, identical combine on every
+        rank.  `safe` / `sample` are full-length [N] masks (or None).  Returns
+        the device record (int64[4]; [0] is the global index)."""
+        if self.comm is None:
+            return self.masked_argmax(F_loc, safe, first_constraint, sample)
+        sl = slice(self.row0, self.row0 + self.n_loc)
+        rec = self.masked_argmax(F_loc, safe[sl] if safe is not None else None, first_constraint,
+                                 sample[sl] if sample is not None else None, idx_offset=self.row0,
+                                 l_offset=self.row0)
+        self.comm.gather_records(rec, self._recs)
+        _abi.check(self.lib.tal_argmax_combine(_ptr(self._recs), self.comm.world,
+                                               _ptr(self._combined), _stream()), "tal_argmax_combine")
+        return self._combined
 
     def read_result(self, result: Optional[torch.Tensor] = None) -> _abi.ArgmaxResult:
         """Device -> host read of an arg-max record (synchronises the stream)."""
