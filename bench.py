@@ -42,6 +42,8 @@ WORKLOADS = {
     # BASELINE.json configs[2]
     "c3": dict(N=65536, m=4096, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=16),
     "c3_small": dict(N=4096, m=256, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=8),
+    # BASELINE.json configs[4]: large-domain ITL, needs the 8 GPUs of one box (fp64: 320 GB of covariance)
+    "c5": dict(N=200000, m=8192, d=4, lengthscale=0.2, rho=0.1, beta=1.0, grid=0),
 }
 METRIC = "BO steps/s (rank-1 update + ITL argmax) at N=65k"
 UNIT = "steps/s"
@@ -55,8 +57,11 @@ def make_problem(w):
     target set A, and a table of noisy observations."""
     g, d, N = w["grid"], w["d"], w["N"]
     rng = np.random.default_rng(0)
-    axes = np.meshgrid(*([np.arange(g) / g] * d), indexing="ij")
-    domain = np.stack(axes, -1).reshape(-1, d)[:N] + rng.random((N, d)) / g
+    if g:
+        axes = np.meshgrid(*([np.arange(g) / g] * d), indexing="ij")
+        domain = np.stack(axes, -1).reshape(-1, d)[:N] + rng.random((N, d)) / g
+    else:  # uniform random domain (SURVEY.md 8d, C5)
+        domain = rng.random((N, d))
     A = np.sort(rng.choice(N, w["m"], replace=False))
     r1 = np.random.default_rng(1)
     noise = r1.standard_normal(N)
@@ -196,8 +201,9 @@ def run_reference(args, w):
 
 def workload_config(args, w, world):
     return {
-        "workload": (f"BASELINE configs[2]: synthetic transductive ITL, N={w['N']} candidates, target set "
-                     f"m={w['m']}, d={w['d']} Matern-5/2 (l={w['lengthscale']}), q=1, rho={w['rho']}, fp64"),
+        "workload": (f"BASELINE configs[{4 if args.workload == 'c5' else 2}]: synthetic transductive ITL, "
+                     f"N={w['N']} candidates, target set m={w['m']}, d={w['d']} Matern-5/2 "
+                     f"(l={w['lengthscale']}), q=1, rho={w['rho']}, fp64"),
         "name": args.workload, "N": w["N"], "m": w["m"], "d": w["d"], "q": 1,
         "conditioning": args.conditioning,
         "l2": "inputs larger than L2 (covariance %.1f GB per GPU >> 126 MB): no flush needed"
@@ -388,6 +394,10 @@ def run_ours(args, w):
     launches = int(lib.tal_launch_count())
     e2e_ms = bench.e2e(args.steps)
     clk = clocks.stop()
+    if os.environ.get("TAL_BREAKDOWN"):
+        bd = bench.breakdown()
+        if rank == 0:
+            sys.stderr.write("breakdown_us " + json.dumps(bd) + "\n")
     if rank == 0:
         total_ms, rank1_ms = float(total_ms), float(rank1_ms)
         alg_bytes = 2.0 * bench.gp.n_loc * bench.gp.ld * 8

@@ -271,8 +271,16 @@ int tal_cond_extract_col(const double* V, long long ldv, long long m_pad, long l
 int tal_cond_update(double* V, long long ldv, long long m_pad, long long ncols, long long n_valid,
                     long long col0, const double* pcol, const void* kbuf_i, const void* wbuf_i,
                     const double* rho_i, const long long* idx_dev, long long idx_host,
-                    void* coef_scratch, double* cs, int dtype, void* stream);
+                    void* coef_scratch, double* cs, int chunks, double* chunk_scratch, int dtype,
+                    void* stream);
 long long tal_cond_coef_bytes(long long m_pad);
+/* chunks: 1 = one pass, every thread walks all m rows of its two columns
+ * (2 m N 8 bytes of traffic; right when there are >= 64k columns); > 1 = the rows
+ * are split into `chunks` chunks handled by different CTAs through the prefix-sum
+ * form of the recurrence (one extra read pass over V, but m/chunks-long serial
+ * chains: right for a shard with few columns); 0 = choose.  chunk_scratch:
+ * tal_cond_chunk_scratch_bytes(ncols) bytes (may be null with chunks <= 1).  */
+long long tal_cond_chunk_scratch_bytes(long long ncols);
 
 /* ---- masked arg-max -----------------------------------------------------
  * Replaces DiscreteGreedyAlgorithm._step's sample-region masking

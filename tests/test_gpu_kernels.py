@@ -389,6 +389,36 @@ def test_incremental_conditioning_matches_recompute(cuda, dtype):
                                fresh.score_itl_directed(roi, m), rtol=tol, atol=tol * 1e-2)
 
 
+@pytest.mark.parametrize("chunks", [2, 8, 32])
+def test_cond_update_row_parallel_matches_single_pass(cuda, chunks):
+    """The prefix-sum (row-parallel) form of the downdate against the one-pass recurrence."""
+    import ctypes as C
+    from talgp import _abi
+    lib = _abi.load()
+    rng = np.random.default_rng(5)
+    m, n = 512, 300
+    Vh = rng.standard_normal((m, n)) * 0.03  # ||p||^2 = ||V[:, x]||^2 / s ~ 0.36 < 1
+    Vh[400:] = 0.0  # pad rows
+    w = rng.standard_normal(n) * 0.3
+    k = np.ones(n); rho = np.full(n, 0.1)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    kd, wd, rd = _dev(k, cuda), _dev(w, cuda), _dev(rho, cuda)  # keep the device buffers alive
+    for ch in (1, chunks):
+        V = _dev(Vh, cuda)
+        pcol = V[:, 17].clone()
+        coef = torch.empty((int(lib.tal_cond_coef_bytes(m)) // 8,), dtype=torch.float64, device=cuda)
+        scratch = torch.empty((int(lib.tal_cond_chunk_scratch_bytes(n)) // 8,), dtype=torch.float64, device=cuda)
+        cs = torch.empty((n,), dtype=torch.float64, device=cuda)
+        _abi.check(lib.tal_cond_update(p(V), n, m, n, n - 4, 0, p(pcol), p(kd), p(wd),
+                                       p(rd), None, 17, p(coef), p(cs), ch, p(scratch), _abi.F64, st))
+        outs.append((V, cs))
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[1][0]).all()
+    torch.testing.assert_close(outs[1][0], outs[0][0], rtol=1e-11, atol=1e-14)
+    torch.testing.assert_close(outs[1][1], outs[0][1], rtol=1e-11, atol=1e-14)
+
+
 def test_potrf_trsm_against_lapack(cuda):
     """The DMMA Cholesky / TRSM on a well-conditioned SPD matrix: 1e-11."""
     import ctypes as C

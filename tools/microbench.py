@@ -141,11 +141,14 @@ def bench_condinc(N, m):
     rho = torch.full((N,), 0.1, dtype=torch.float64, device=dev)
     coef = torch.empty((int(lib.tal_cond_coef_bytes(m)) // 8,), dtype=torch.float64, device=dev)
     cs = torch.empty((N,), dtype=torch.float64, device=dev)
-    med, mn = time_ms(lambda: _abi.check(lib.tal_cond_update(
-        _ptr(V), N, m, N, N, 0, _ptr(pcol), _ptr(kbuf), _ptr(wbuf), _ptr(rho), None, 777, _ptr(coef),
-        _ptr(cs), _abi.F64, _stream())), warm=2, reps=10)
-    emit(kernel="cond_update(+coeffs)", m=m, N=N, ms=med, ms_min=mn, GBs=2 * m * N * 8 / med / 1e6,
-         frac_of_measured=2 * m * N * 8 / med / 1e6 / PEAK)
+    chunk = torch.empty((int(lib.tal_cond_chunk_scratch_bytes(N)) // 8,), dtype=torch.float64, device=dev)
+    for ncols in (N, N // 2, N // 8):
+        for chunks in (1, 2, 4, 8, 16, 32):
+            med, mn = time_ms(lambda: _abi.check(lib.tal_cond_update(
+                _ptr(V), N, m, ncols, ncols, 0, _ptr(pcol), _ptr(kbuf), _ptr(wbuf), _ptr(rho), None, 777,
+                _ptr(coef), _ptr(cs), chunks, _ptr(chunk), _abi.F64, _stream())), warm=2, reps=6)
+            emit(kernel="cond_update(+coeffs)", m=m, ncols=ncols, chunks=chunks, ms=med, ms_min=mn,
+                 GBs_2pass=2 * m * ncols * 8 / med / 1e6)
 
 
 def bench_probe():

@@ -29,6 +29,13 @@ namespace tal {
 struct alignas(32) CondCoef {
   double p, a, b, d;
 };
+// the same downdate written as a prefix sum (used when the rows are split over
+// several CTAs): sigma_j = P_j / gamma_j with P_j = sum_{i<j} p_i y_i, because
+// row j of T is -p_j p_{<j}^T T_{<j}^-T / T_jj and
+// p_{<j}^T (I - p_{<j} p_{<j}^T)^-1 y_{<j} = (p_{<j}^T y_{<j}) / gamma_j.
+struct alignas(32) CondCoef2 {
+  double p, d, ginv, vx;
+};
 
 // pcol[j] = V[j][col] if this shard owns the column, else 0 (sum over shards = broadcast)
 __global__ void __launch_bounds__(256)
@@ -45,7 +52,7 @@ template <typename T>
 __global__ void __launch_bounds__(1024)
 cond_coeffs_kernel(const double* __restrict__ pcol, i64 m_pad, const T* __restrict__ kbuf,
                    const double* __restrict__ rho, const i64* __restrict__ idx_dev, i64 idx_host,
-                   CondCoef* __restrict__ coef) {
+                   CondCoef* __restrict__ coef, CondCoef2* __restrict__ coef2) {
   __shared__ double wsum[32];
   __shared__ double carry_sh;
   const i64 idx = idx_dev ? *idx_dev : idx_host;
@@ -79,6 +86,12 @@ cond_coeffs_kernel(const double* __restrict__ pcol, i64 m_pad, const T* __restri
       c.b = cj * c.d;
       c.a = 1.0 + c.b * p;
       coef[j] = c;
+      CondCoef2 c2;
+      c2.p = p;
+      c2.d = c.d;
+      c2.ginv = 1.0 / g0;
+      c2.vx = pcol[j];
+      coef2[j] = c2;
     }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry_sh = incl;
@@ -132,6 +145,93 @@ cond_update_kernel(double* __restrict__ V, i64 ldv, i64 m_pad, i64 ncols, i64 n_
   cs[col + 1] = q1;
 }
 
+// ---- row-parallel form: the m rows are split into chunks of CH rows --------
+// pass 1: tot[c][x] = sum_{i in chunk c} p_i y_i[x],  y_i[x] = V[i][x] - vx_i w[x]
+template <typename T>
+__global__ void __launch_bounds__(128)
+cond_chunk_totals_kernel(const double* __restrict__ V, i64 ldv, int CH, i64 ncols, i64 n_valid,
+                         i64 col0, const CondCoef2* __restrict__ coef, const T* __restrict__ wbuf,
+                         double* __restrict__ tot) {
+  const i64 col = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (col >= ncols) return;
+  const double w0 = col < n_valid ? (double)wbuf[col0 + col] : 0.0;
+  const double w1 = col + 1 < n_valid ? (double)wbuf[col0 + col + 1] : 0.0;
+  const i64 j0 = (i64)blockIdx.y * CH;
+  const double2* Vp = reinterpret_cast<const double2*>(V + col);
+  const i64 ldv2 = ldv / 2;
+  double t0 = 0.0, t1 = 0.0;
+  for (int j = 0; j < CH; j += 8) {
+    double2 y[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) y[t] = ld_stream(Vp + (j0 + j + t) * ldv2);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const CondCoef2 c = coef[j0 + j + t];
+      t0 += c.p * (y[t].x - c.vx * w0);
+      t1 += c.p * (y[t].y - c.vx * w1);
+    }
+  }
+  tot[(i64)blockIdx.y * ncols + col] = t0;
+  tot[(i64)blockIdx.y * ncols + col + 1] = t1;
+}
+
+// pass 2: within chunk c start from P = sum_{c' < c} tot[c'][x] and apply
+// z_j = d_j (y_j + p_j P_j / gamma_j), P_{j+1} = P_j + p_j y_j; csp[c][x] = sum z^2.
+template <typename T>
+__global__ void __launch_bounds__(128)
+cond_chunk_apply_kernel(double* __restrict__ V, i64 ldv, int CH, i64 ncols, i64 n_valid, i64 col0,
+                        const CondCoef2* __restrict__ coef, const T* __restrict__ wbuf,
+                        const double* __restrict__ tot, double* __restrict__ csp) {
+  const i64 col = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (col >= ncols) return;
+  const double w0 = col < n_valid ? (double)wbuf[col0 + col] : 0.0;
+  const double w1 = col + 1 < n_valid ? (double)wbuf[col0 + col + 1] : 0.0;
+  const i64 j0 = (i64)blockIdx.y * CH;
+  double P0 = 0.0, P1 = 0.0;
+  for (int c = 0; c < (int)blockIdx.y; ++c) {  // fixed order: deterministic
+    const double2 t = *reinterpret_cast<const double2*>(tot + (i64)c * ncols + col);
+    P0 += t.x;
+    P1 += t.y;
+  }
+  double2* Vp = reinterpret_cast<double2*>(V + col);
+  const i64 ldv2 = ldv / 2;
+  double q0 = 0.0, q1 = 0.0;
+  double2 y[8], yn[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) y[t] = ld_stream(Vp + (j0 + t) * ldv2);
+  for (int j = 0; j < CH; j += 8) {
+    if (j + 8 < CH) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) yn[t] = ld_stream(Vp + (j0 + j + 8 + t) * ldv2);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const CondCoef2 c = coef[j0 + j + t];
+      const double y0 = y[t].x - c.vx * w0, y1 = y[t].y - c.vx * w1;
+      const double pg = c.p * c.ginv;
+      const double z0 = c.d * (y0 + pg * P0), z1 = c.d * (y1 + pg * P1);
+      P0 += c.p * y0;
+      P1 += c.p * y1;
+      q0 += z0 * z0;
+      q1 += z1 * z1;
+      st_stream(Vp + (j0 + j + t) * ldv2, make_double2(z0, z1));
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) y[t] = yn[t];
+  }
+  csp[(i64)blockIdx.y * ncols + col] = q0;
+  csp[(i64)blockIdx.y * ncols + col + 1] = q1;
+}
+
+__global__ void __launch_bounds__(256)
+cond_sum_chunks_kernel(const double* __restrict__ csp, int R, i64 ncols, double* __restrict__ cs) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= ncols) return;
+  double acc = 0.0;
+  for (int c = 0; c < R; ++c) acc += csp[(i64)c * ncols + x];
+  cs[x] = acc;
+}
+
 }  // namespace tal
 
 using namespace tal;
@@ -149,33 +249,68 @@ int tal_cond_extract_col(const double* V, long long ldv, long long m_pad, long l
 }
 
 int tal_cond_update(double* V, long long ldv, long long m_pad, long long ncols, long long n_valid,
-                    long long col0,
-                    const double* pcol, const void* kbuf_i, const void* wbuf_i, const double* rho_i,
-                    const long long* idx_dev, long long idx_host, void* coef_scratch, double* cs,
-                    int dtype, void* stream) {
+                    long long col0, const double* pcol, const void* kbuf_i, const void* wbuf_i,
+                    const double* rho_i, const long long* idx_dev, long long idx_host,
+                    void* coef_scratch, double* cs, int chunks, double* chunk_scratch, int dtype,
+                    void* stream) {
   TAL_ARG(V && pcol && kbuf_i && wbuf_i && rho_i && coef_scratch && cs && n_valid <= ncols);
-  TAL_ARG(m_pad >= 8 && m_pad % 8 == 0 && ncols >= 2 && ncols % 2 == 0 && ldv >= ncols && ldv % 2 == 0);
+  TAL_ARG(m_pad >= 128 && m_pad % 128 == 0 && ncols >= 2 && ncols % 2 == 0 && ldv >= ncols && ldv % 2 == 0);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(chunks >= 0 && (chunks <= 1 || chunk_scratch));
   cudaStream_t st = as_stream(stream);
   CondCoef* coef = (CondCoef*)coef_scratch;
+  CondCoef2* coef2 = (CondCoef2*)(coef + m_pad);
   if (dtype == TAL_F64)
     cond_coeffs_kernel<double><<<1, 1024, 0, st>>>(pcol, m_pad, (const double*)kbuf_i, rho_i,
-                                                   idx_dev, idx_host, coef);
+                                                   idx_dev, idx_host, coef, coef2);
   else
     cond_coeffs_kernel<float><<<1, 1024, 0, st>>>(pcol, m_pad, (const float*)kbuf_i, rho_i, idx_dev,
-                                                  idx_host, coef);
+                                                  idx_host, coef, coef2);
   TAL_LAUNCH_CHECK("tal_cond_update/coeffs");
-  const unsigned grid = (unsigned)((ncols / 2 + 63) / 64);
-  if (dtype == TAL_F64)
-    cond_update_kernel<double, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
-                                                        (const double*)wbuf_i, cs);
-  else
-    cond_update_kernel<float, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef, pcol,
-                                                       (const float*)wbuf_i, cs);
-  TAL_LAUNCH_CHECK("tal_cond_update");
+  if (chunks == 0) {  // auto (measured, profiles/): >= 64k columns fill the machine in one pass
+    chunks = 1;
+    if (ncols < 60000 && chunk_scratch)
+      while (chunks < 32 && m_pad / (chunks * 2) >= 64 && (m_pad / (chunks * 2)) % 8 == 0) chunks *= 2;
+  }
+  if (chunks <= 1) {
+    const unsigned grid = (unsigned)((ncols / 2 + 63) / 64);
+    if (dtype == TAL_F64)
+      cond_update_kernel<double, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef,
+                                                         pcol, (const double*)wbuf_i, cs);
+    else
+      cond_update_kernel<float, 8><<<grid, 64, 0, st>>>(V, ldv, m_pad, ncols, n_valid, col0, coef,
+                                                        pcol, (const float*)wbuf_i, cs);
+    TAL_LAUNCH_CHECK("tal_cond_update");
+    return TAL_OK;
+  }
+  TAL_ARG(m_pad % chunks == 0 && (m_pad / chunks) % 8 == 0);
+  const int CH = (int)(m_pad / chunks);
+  double* tot = chunk_scratch;
+  double* csp = chunk_scratch + (i64)chunks * ncols;
+  dim3 grid((unsigned)((ncols / 2 + 127) / 128), (unsigned)chunks);
+  if (dtype == TAL_F64) {
+    cond_chunk_totals_kernel<double><<<grid, 128, 0, st>>>(V, ldv, CH, ncols, n_valid, col0, coef2,
+                                                          (const double*)wbuf_i, tot);
+    TAL_LAUNCH_CHECK("tal_cond_update/totals");
+    cond_chunk_apply_kernel<double><<<grid, 128, 0, st>>>(V, ldv, CH, ncols, n_valid, col0, coef2,
+                                                         (const double*)wbuf_i, tot, csp);
+  } else {
+    cond_chunk_totals_kernel<float><<<grid, 128, 0, st>>>(V, ldv, CH, ncols, n_valid, col0, coef2,
+                                                         (const float*)wbuf_i, tot);
+    TAL_LAUNCH_CHECK("tal_cond_update/totals");
+    cond_chunk_apply_kernel<float><<<grid, 128, 0, st>>>(V, ldv, CH, ncols, n_valid, col0, coef2,
+                                                        (const float*)wbuf_i, tot, csp);
+  }
+  TAL_LAUNCH_CHECK("tal_cond_update/apply");
+  cond_sum_chunks_kernel<<<(unsigned)((ncols + 255) / 256), 256, 0, st>>>(csp, chunks, ncols, cs);
+  TAL_LAUNCH_CHECK("tal_cond_update/sum");
   return TAL_OK;
 }
 
-long long tal_cond_coef_bytes(long long m_pad) { return m_pad * (long long)sizeof(CondCoef); }
+long long tal_cond_coef_bytes(long long m_pad) {
+  return m_pad * (long long)(sizeof(CondCoef) + sizeof(CondCoef2));
+}
+
+long long tal_cond_chunk_scratch_bytes(long long ncols) { return 2LL * 32 * ncols * (long long)sizeof(double); }
 
 }  // extern "C"

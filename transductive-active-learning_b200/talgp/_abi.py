@@ -75,8 +75,10 @@ SIGNATURES = {
     "tal_colsumsq_dense": (_i, [_p, _ll, _ll, _ll, _p, _i, _p, _p]),
     "tal_score_itl_directed": (_i, [_p, _p, _p, _ll, _i, _p, _p]),
     "tal_cond_extract_col": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p]),
-    "tal_cond_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _ll, _p, _p, _i, _p]),
+    "tal_cond_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _ll, _p, _p, _i, _p,
+                             _i, _p]),
     "tal_cond_coef_bytes": (_ll, [_ll]),
+    "tal_cond_chunk_scratch_bytes": (_ll, [_ll]),
     "tal_argmax_scratch_bytes": (_ll, []),
     "tal_masked_argmax": (_i, [_p, _p, _p, _i, _i, _ll, _p, _ll, _ll, _p, _p, _p]),
     "tal_argmax_combine": (_i, [_p, _i, _p, _p]),

@@ -169,6 +169,45 @@ class ShardedITLBench:
     def _select(self):
         return self.gp.argmax_candidates(self.score(), None, 1, None)
 
+    def breakdown(self, steps: int = 10):
+        """Per-phase device times of one step (CUDA events; diagnostic)."""
+        gp = self.gp
+        names = ["score", "argmax_local", "gather+combine", "extract_row", "sum(kbuf)", "step_vectors",
+                 "cond_extract", "sum(pcol)", "cond_update", "rank1_update"]
+        acc = np.zeros(len(names))
+        for _ in range(steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ev[0].record()
+            F = self.score(); ev[1].record()
+            sl = slice(gp.row0, gp.row0 + gp.n_loc)
+            rec = gp.masked_argmax(F, None, 1, None, idx_offset=gp.row0, l_offset=gp.row0); ev[2].record()
+            if gp.comm is not None:
+                from . import _abi
+                from .engine import _ptr, _stream
+                gp.comm.gather_records(rec, gp._recs)
+                _abi.check(gp.lib.tal_argmax_combine(_ptr(gp._recs), gp.comm.world, _ptr(gp._combined), _stream()))
+                rec = gp._combined
+            ev[3].record()
+            idx_dev = rec[0:1]
+            gp.extract_row(idx_dev); ev[4].record()
+            gp._sum(gp.kbuf); ev[5].record()
+            gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta); ev[6].record()
+            st = gp._cond
+            from . import _abi
+            from .engine import _ptr, _stream
+            _abi.check(gp.lib.tal_cond_extract_col(_ptr(st["V"][0]), st["ncols"], st["m_pad"], gp.row0, gp.n_loc,
+                                                   _ptr(idx_dev), 0, _ptr(st["pcol"]), _stream())); ev[7].record()
+            gp._sum(st["pcol"]); ev[8].record()
+            _abi.check(gp.lib.tal_cond_update(_ptr(st["V"][0]), st["ncols"], st["m_pad"], st["ncols"], gp.n_loc,
+                                              gp.row0, _ptr(st["pcol"]), _ptr(gp.kbuf[0]), _ptr(gp.wbuf[0]),
+                                              _ptr(gp.rho[0]), _ptr(idx_dev), 0, _ptr(st["coef"]),
+                                              _ptr(st["cs"][0]), int(gp.cond_chunks), _ptr(st["chunk"]),
+                                              gp.dt, _stream())); ev[9].record()
+            gp.rank1_update(); ev[10].record()
+            torch.cuda.synchronize()
+            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        return dict(zip(names, (acc / steps * 1e3).round(1).tolist()))  # microseconds
+
     def step(self, record: bool) -> None:
         rec = self._select()
         idx_dev = rec[0:1]

@@ -100,6 +100,7 @@ class DeviceGP:
         self._y_dev = torch.zeros((q,), **f64)
         self._ws = {}  # named scratch tensors, grown on demand
         self._cond = None  # incremental conditioning state (score_itl_directed)
+        self.cond_chunks = 0  # tal_cond_update: 0 = choose, 1 = single pass, > 1 = row-parallel
         if self.comm is not None:
             self._recs = torch.zeros((self.comm.world, 4), dtype=torch.int64, device=dev)
             self._combined = torch.zeros((4,), dtype=torch.int64, device=dev)
@@ -420,7 +421,9 @@ class DeviceGP:
                           cs=torch.empty((self.q, ncols), dtype=torch.float64, device=self.device),
                           pcol=torch.empty((m_pad,), dtype=torch.float64, device=self.device),
                           coef=torch.empty((int(self.lib.tal_cond_coef_bytes(m_pad)) // 8,),
-                                           dtype=torch.float64, device=self.device))
+                                           dtype=torch.float64, device=self.device),
+                          chunk=torch.empty((int(self.lib.tal_cond_chunk_scratch_bytes(ncols)) // 8,),
+                                            dtype=torch.float64, device=self.device))
             st.update(key=roi_key, m_pad=m_pad, ncols=ncols, valid=False)
             self._cond = st
         if not incremental and st is not None:
@@ -451,8 +454,8 @@ class DeviceGP:
             _abi.check(self.lib.tal_cond_update(
                 _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_loc, self.row0,
                 _ptr(st["pcol"]), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
-                _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]), self.dt,
-                _stream()), "tal_cond_update")
+                _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]),
+                int(self.cond_chunks), _ptr(st["chunk"]), self.dt, _stream()), "tal_cond_update")
 
     def drop_conditioning(self) -> None:
         self._cond = None
