@@ -14,11 +14,19 @@ Pinning status (see DESIGN.md "Oracle"):
     noise_covariance_matrix, solve_linear_system, log_prob) and the exact
     prior-state checks of tests/test_discrete_model.py:29-39 and
     tests/test_continuous_model.py:30-40.
-  * PARITY UNPINNED for MarginalModel.step / posterior, ITL.F, VTL.F, the
-    safe-set masks and objective_argmax: the reference's tests hold no vectors
-    for them and the reference itself cannot be imported in this image (jax,
-    jaxlib, chex, optax, matplotlib absent; no network), so no fixtures could
-    be generated from it.  Those functions are restated from the source and
-    cross-checked only through mathematical identities (tests/test_oracle.py).
+  * PINNED against outputs of the reference's OWN SOURCE run in the build
+    container: /root/reference/lib is imported and executed over a NumPy
+    stand-in for jax.numpy / jax.random / chex (tests/golden/refshim.py; jax and
+    jaxlib 0.4.30 are absent and not installable).  The committed vectors
+    (tests/golden/reference_calls.npz, reference_trajectories.npz, generator
+    tests/golden/make_reference_fixtures.py) cover the kernels, get_indices /
+    get_mask / is_subset_of, compute_posterior_covariance / posterior,
+    MarginalModel.step (m = 0, 1, 5, heteroscedastic noise, callable beta), all
+    safe-set masks, sqd_correlation, objective_argmax (messages, tie set) and
+    eight BO trajectories (ITL, VTL, CTL, MM-ITL with PM / fixed ROIs);
+    tests/test_reference_fixtures.py holds the oracle to them at 1e-10.
+    What those vectors do NOT pin is XLA's own arithmetic (fusion, Eigen's
+    summation order, threefry draws): rounding-level differences and the choice
+    among exact ties (jr.choice) remain documented, not reproduced.
 """
 from .ref_numpy import *  # noqa: F401,F403

@@ -65,7 +65,7 @@ def c4(T=10):
 ALL = {"c1": c1, "c2": c2, "c3": c3, "c4": c4}
 
 
-def build_oracle(p):
+def build_oracle(p, rule=None):
     import oracle as O
     q = len(p["kernels"])
     ks = [getattr(O, k)(variance=v, lengthscale=l) for k, v, l in p["kernels"]]
@@ -78,13 +78,15 @@ def build_oracle(p):
     else:
         A = p["roi"]
         ctor = lambda m: m.domain[A]
-    alg = {"ITL": O.ITL, "VTL": O.VTL}[p["rule"]](model, ctor)
+    alg = {"ITL": O.ITL, "VTL": O.VTL, "CTL": O.CTL, "MMITL": O.MMITL}[rule or p["rule"]](model, ctor)
     return model, alg, O.TableFunction(p["domain"], p["table"])
 
 
-def build_cuda(p, comm=None, **alg_kw):
+def build_cuda(p, comm=None, rule=None, **alg_kw):
     from lib.algorithms import index_roi_constructor, pe_roi_constructor, pm_roi_constructor
+    from lib.algorithms.ctl import CTL
     from lib.algorithms.itl import ITL
+    from lib.algorithms.mm_itl import MMITL
     from lib.algorithms.vtl import VTL
     from lib.function import TableFunction
     from lib.gp.kernels import stationary
@@ -102,5 +104,5 @@ def build_cuda(p, comm=None, **alg_kw):
         ctor = {"pm": pm_roi_constructor, "pe": pe_roi_constructor}[p["roi"]]
     else:
         ctor = index_roi_constructor(p["roi"])
-    alg = {"ITL": ITL, "VTL": VTL}[p["rule"]](model, ctor, **alg_kw)
+    alg = {"ITL": ITL, "VTL": VTL, "CTL": CTL, "MMITL": MMITL}[rule or p["rule"]](model, ctor, **alg_kw)
     return model, alg, TableFunction(model.domain, p["table"], first_constraint=model.first_constraint)
