@@ -394,6 +394,11 @@ def run_ours(args, w):
     launches = int(lib.tal_launch_count())
     e2e_ms = bench.e2e(args.steps)
     clk = clocks.stop()
+    exchange = "nccl"
+    if getattr(bench.gp.comm, "peer", False):
+        exchange = "nvlink-peer-memory"
+        err = bench.gp.comm.error()
+        assert err == 0, f"peer exchange timed out (TAL_PEER_ERR {err})"
     if os.environ.get("TAL_BREAKDOWN"):
         bd = bench.breakdown()
         if rank == 0:
@@ -406,7 +411,7 @@ def run_ours(args, w):
             "metric": METRIC, "value": args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args, w, world),
+            "data": "synthetic", "config": dict(workload_config(args, w, world), exchange=exchange),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8,
                     "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TAL_ABI_VERSION 1
+#define TAL_ABI_VERSION 2
 #define TAL_MAX_Q 16
 
 /* status codes */
@@ -302,6 +302,53 @@ int tal_masked_argmax(double* F_io, const unsigned char* safe, const double* l, 
  * combined) — the all-reduce of the per-shard arg-max after an all-gather. */
 int tal_argmax_combine(const tal_argmax_result* parts, int G, tal_argmax_result* out,
                        void* stream);
+
+/* ---- exchange steps over NVLink peer memory (row-sharded model) ----
+ * One process per GPU.  Every rank owns a MAILBOX: one device allocation
+ * (tal_peer_alloc) laid out as [header: tal_peer_header_bytes()][kbuf: q*ld
+ * elements at kbuf_off][pcol: q*m_pad doubles at pcol_off] (offsets chosen by
+ * the caller, multiples of 256), exported with tal_peer_export (a CUDA IPC
+ * handle, exchanged by the host over any channel) and mapped by the peers with
+ * tal_peer_import.  `mailboxes` is a DEVICE array of the G mailbox pointers as
+ * seen from this rank (entry `rank` = its own).  The kernels replace the two
+ * NCCL calls of a step (all-gather of the arg-max records; broadcast of the
+ * observed row, lib/gp/gaussian_distribution.py:33 `Kxt`) by P2P stores plus
+ * release/acquire sequence numbers kept in the mailboxes; every rank must
+ * issue the same call sequence.  Counters advance on the device, so the launch
+ * sequence of a step is capturable in a CUDA graph.  Spins are bounded: on
+ * expiry the mailbox error word becomes TAL_PEER_ERR_* (tal_peer_error).      */
+#define TAL_PEER_MAX 16
+#define TAL_PEER_HANDLE_BYTES 64
+#define TAL_PEER_ERR_RECORD_TIMEOUT 1
+#define TAL_PEER_ERR_READY_TIMEOUT 2
+#define TAL_PEER_ERR_ROW_TIMEOUT 3
+long long tal_peer_header_bytes(void);
+int tal_peer_alloc(long long bytes, void** ptr_host);           /* zero-filled */
+int tal_peer_free(void* ptr);
+int tal_peer_export(void* ptr, unsigned char* handle_host);     /* TAL_PEER_HANDLE_BYTES */
+int tal_peer_import(const unsigned char* handle_host, void** ptr_host);
+int tal_peer_unimport(void* ptr);
+int tal_peer_enable_access(int peer_device);                    /* same-process peers */
+/* all-gather of the per-shard arg-max records: publish = store `rec` into slot
+ * `rank` of every mailbox; combine = wait for the G records of this exchange in
+ * the own mailbox and reduce them like tal_argmax_combine.                      */
+int tal_peer_publish_record(const tal_argmax_result* rec, void* const* mailboxes, int G, int rank,
+                            void* stream);
+int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void* stream);
+/* broadcast of the observed row: the owner (idx / rows_per_rank) waits until
+ * every rank has signalled that its row buffer is free, then stores
+ * cov[:, idx - row0, :] into every mailbox's kbuf and, if V != null, the column
+ * V[:, :, idx - row0] (V is [q][m_pad][ldv] fp64, the incremental-conditioning
+ * state) into every mailbox's pcol; tal_peer_wait_row blocks the stream until the
+ * data of this exchange has landed and writes scal[i] = mean[i][idx].           */
+int tal_peer_push_row(void* const* mailboxes, int G, int rank, long long rows_per_rank, const void* cov,
+                      long long cov_stride_q, long long ld, long long row0, long long n_loc, int q,
+                      const long long* idx_dev, long long idx_host, long long kbuf_off,
+                      const double* V, long long v_stride_q, long long ldv, long long m_pad,
+                      long long pcol_off, int dtype, void* stream);
+int tal_peer_wait_row(void* mailbox, const long long* idx_dev, long long idx_host, const double* mean,
+                      long long N, int q, double* scal, void* stream);
+int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synchronises */
 
 /* ---- fp64 peak probes (roofline denominators of the tensor path) --------
  * kind 0: DMMA.8x8x4, kind 1: DFMA; `blocks` CTAs x 256 threads x iters x 16

@@ -12,25 +12,36 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning):
-    from talgp.dist import ShardedITLBench, ThreadComm
+def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="thread"):
+    from talgp.dist import LocalPeerComm, ShardedITLBench, ThreadComm
     shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
     out = [None] * G
     errs = []
 
+    def body(rank):
+        comm = ThreadComm(shared, rank, G) if exchange == "thread" else LocalPeerComm(shared, rank, G)
+        b = ShardedITLBench(domain, A, table, w, G, rank, cuda, conditioning, comm=comm)
+        sel, Fs = [], []
+        for t in range(steps):
+            F = b.score()
+            Fs.append(F.clone())
+            rec = b.gp.argmax_candidates(F, None, 1, None)
+            sel.append(int(rec[0].item()))
+            b.gp.observe(rec[0:1], b.table, b.beta, y_gather=True, y_stride=w["N"])
+        if exchange == "peer":
+            torch.cuda.current_stream().synchronize()
+            assert comm.error() == 0
+        out[rank] = (b, sel, Fs)
+
     def worker(rank):
         try:
             torch.cuda.set_device(cuda)
-            b = ShardedITLBench(domain, A, table, w, G, rank, cuda, conditioning,
-                                comm=ThreadComm(shared, rank, G))
-            sel, Fs = [], []
-            for t in range(steps):
-                F = b.score()
-                Fs.append(F.clone())
-                rec = b.gp.argmax_candidates(F, None, 1, None)
-                sel.append(int(rec[0].item()))
-                b.gp.observe(rec[0:1], b.table, b.beta, y_gather=True, y_stride=w["N"])
-            out[rank] = (b, sel, Fs)
+            if exchange == "peer":  # the shards' kernels wait on each other: one stream per shard
+                with torch.cuda.stream(torch.cuda.Stream(device=cuda)):
+                    body(rank)
+                    torch.cuda.current_stream().synchronize()
+            else:
+                body(rank)
         except Exception as e:  # pragma: no cover
             errs.append(e)
             shared["barrier"].abort()
@@ -43,9 +54,13 @@ def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning):
     return out
 
 
+@pytest.mark.parametrize("exchange", ["thread", "peer"])
 @pytest.mark.parametrize("conditioning", ["incremental", "recompute"])
 @pytest.mark.parametrize("G", [2, 3])
-def test_sharded_itl_matches_single_gpu(cuda, G, conditioning):
+def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange):
+    """exchange="thread": host-emulated collectives on one stream; "peer": the NVLink
+    peer-memory protocol of csrc/peer.cu (mailboxes, P2P stores, release/acquire
+    sequence numbers) between shards running concurrently on their own streams."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import make_problem
@@ -68,7 +83,7 @@ def test_sharded_itl_matches_single_gpu(cuda, G, conditioning):
         rec = gp.masked_argmax(F, None, 1, None)
         sel1.append(int(rec[0].item()))
         gp.observe(rec[0:1].clone(), tab, [1.0], y_gather=True, y_stride=N)
-    out = _run_sharded(cuda, G, domain, A, table, w, steps, conditioning)
+    out = _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange)
     # every rank saw the same selections, equal to the single-GPU run
     for b, sel, Fs in out:
         assert sel == sel1

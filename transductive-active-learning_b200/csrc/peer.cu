@@ -1,0 +1,348 @@
+// Exchange steps of the row-sharded model over NVLink peer memory.
+//
+// One process per GPU; every rank owns a "mailbox" (one cudaMalloc, exported
+// with cudaIpcGetMemHandle and mapped by the peers) and a device table of the G
+// mailbox pointers.  The two per-step exchanges then need no NCCL call and no
+// host-known root:
+//
+//   arg-max      every rank STORES its 32-byte record into slot[rank] of every
+//                peer's mailbox (NVLink P2P stores), releases a sequence number;
+//                every rank spins on its own slots and combines (same rule as
+//                tal_argmax_combine) — an all-gather in one hop.
+//   observed row every rank tells the owner of row x* "ready" (it has finished
+//                the previous update, so its row buffer may be overwritten);
+//                the owner waits for the G readies, STORES Sigma[x*, :] (and
+//                V[:, x*] of the incremental conditioning) into every peer's row
+//                buffer and releases a sequence number; the others spin on it.
+//
+// All counters live in device memory and advance inside the kernels, so a step
+// is a fixed launch sequence (CUDA-graph capturable).  Spins are bounded
+// (kSpinTimeoutNs): on expiry the mailbox error word is set and the kernel
+// returns instead of hanging the GPU.
+#include "common.cuh"
+#include <cstring>
+
+namespace tal {
+
+constexpr int kPeerMax = TAL_PEER_MAX;
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct alignas(64) PeerSlot {
+  tal_argmax_result rec;       // 32 B
+  unsigned long long seq;      // exchange number this record belongs to
+  unsigned long long pad[3];
+};
+
+struct alignas(256) PeerHeader {
+  unsigned long long rec_step;  // arg-max exchanges completed by THIS rank
+  unsigned long long row_step;  // row exchanges completed by THIS rank
+  unsigned long long row_seq;   // written by the owner: row exchange whose data has landed
+  unsigned int ticket;          // last-block election of the push kernel
+  int error;                    // != 0: a spin timed out (TAL_PEER_ERR_*)
+  unsigned long long pad0[4];
+  unsigned long long ready[kPeerMax];  // ready[g] = s: rank g may receive row exchange s
+  PeerSlot slot[2][kPeerMax];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// spin until *p == want; false on timeout
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
+  if (ld_acquire_sys(p) == want) return true;
+  const unsigned long long t0 = now_ns();
+  for (;;) {
+    for (int i = 0; i < 64; ++i)
+      if (ld_acquire_sys(p) == want) return true;
+    if (now_ns() - t0 > kSpinTimeoutNs) return false;
+    __nanosleep(100);
+  }
+}
+
+__device__ __forceinline__ PeerHeader* hdr(void* mailbox) { return reinterpret_cast<PeerHeader*>(mailbox); }
+
+// ---- arg-max all-gather ----------------------------------------------------
+// One warp: lane g publishes this rank's record to peer g.
+__global__ void peer_publish_kernel(const tal_argmax_result* __restrict__ rec, void* const* __restrict__ boxes,
+                                    int G, int rank) {
+  const int g = threadIdx.x;
+  if (g >= G) return;
+  const unsigned long long s = hdr(boxes[rank])->rec_step + 1;  // local, stream-ordered
+  PeerSlot* dst = &hdr(boxes[g])->slot[s & 1][rank];
+  const int4* src = reinterpret_cast<const int4*>(rec);
+  int4* d4 = reinterpret_cast<int4*>(&dst->rec);
+  d4[0] = src[0];
+  d4[1] = src[1];
+  __threadfence_system();
+  st_release_sys(&dst->seq, s);
+}
+
+// One warp: lane g waits for rank g's record, then the records are combined
+// (max value, lowest index among equals, tie counts add, flags OR).
+__global__ void peer_combine_kernel(void* mailbox, int G, tal_argmax_result* __restrict__ out) {
+  PeerHeader* h = hdr(mailbox);
+  const unsigned long long s = h->rec_step + 1;
+  const int g = threadIdx.x;
+  double val = -INFINITY;
+  i64 idx = 0x7fffffffffffffffLL, cnt = 0;
+  int flags = 0;
+  bool ok = true;
+  if (g < G) {
+    PeerSlot* sl = &h->slot[s & 1][g];
+    ok = spin_until(&sl->seq, s);
+    const volatile tal_argmax_result* r = &sl->rec;
+    val = r->val; idx = r->idx; cnt = r->n_ties; flags = r->flags;
+    if (cnt == 0) { val = -INFINITY; idx = 0x7fffffffffffffffLL; }
+  }
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (g == 0) h->error = TAL_PEER_ERR_RECORD_TIMEOUT;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v2 = __shfl_xor_sync(0xffffffffu, val, o);
+    const i64 i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    const i64 c2 = __shfl_xor_sync(0xffffffffu, cnt, o);
+    const int f2 = __shfl_xor_sync(0xffffffffu, flags, o);
+    flags |= f2;
+    if (c2 == 0 || (cnt != 0 && val > v2)) {
+    } else if (cnt == 0 || v2 > val) {
+      val = v2; idx = i2; cnt = c2;
+    } else {
+      idx = idx < i2 ? idx : i2; cnt += c2;
+    }
+  }
+  if (g == 0) {
+    out->idx = cnt ? idx : -1;
+    out->val = val;
+    out->n_ties = cnt;
+    out->flags = flags;
+    out->status = !(flags & 1) ? TAL_ARGMAX_EMPTY_SAFE_SET
+                  : !(flags & 2) ? TAL_ARGMAX_ALL_NEG_INF
+                  : !(flags & 4) ? TAL_ARGMAX_ALL_NAN : TAL_ARGMAX_OK;
+    h->rec_step = s;
+  }
+}
+
+// ---- observed-row broadcast --------------------------------------------------
+// grid (ceil(max(ld, m_pad) / (256 * EPT)), q).  Every rank runs it; only the
+// owner of row idx moves data.
+template <typename T, int EPT>
+__global__ void __launch_bounds__(256)
+peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, i64 rows_per_rank,
+                     const T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
+                     const i64* __restrict__ idx_dev, i64 idx_host,
+                     i64 kbuf_off,  // byte offset of kbuf [q][ld] inside a mailbox
+                     const double* __restrict__ V, i64 v_stride_q, i64 ldv, i64 m_pad,
+                     i64 pcol_off) {  // byte offset of pcol [q][m_pad] inside a mailbox (V != null)
+  __shared__ bool s_last;
+  __shared__ int s_ok;
+  const int gp = blockIdx.y;
+  const i64 idx = idx_dev ? *idx_dev : idx_host;
+  PeerHeader* me = hdr(boxes[rank]);
+  const unsigned long long s = me->row_step + 1;
+  int owner = (int)(idx / rows_per_rank);
+  if (owner < 0 || owner >= G) owner = 0;  // invalid index (failed arg-max): keep the protocol moving
+  if (blockIdx.x == 0 && gp == 0 && threadIdx.x == 0)
+    st_release_sys(&hdr(boxes[owner])->ready[rank], s);  // my row buffer is free for exchange s
+  if (owner != rank) return;
+  // owner: wait until every rank is ready to receive
+  if (threadIdx.x < 32) {
+    bool ok = true;
+    if ((int)threadIdx.x < G) ok = spin_until(&me->ready[threadIdx.x], s);
+    ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_ok && threadIdx.x == 0) me->error = TAL_PEER_ERR_READY_TIMEOUT;
+  const i64 r = idx - row0;
+  const bool valid = r >= 0 && r < n_loc;
+  const i64 base = ((i64)blockIdx.x * 256 + threadIdx.x) * EPT;
+  // the row Sigma[x*, :] of GP gp
+  if (base < ld) {
+    T v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) v[j] = (valid && base + j < ld) ? cov[gp * stride_q + r * ld + base + j] : T(0);
+    for (int g = 0; g < G; ++g) {
+      T* dst = reinterpret_cast<T*>(reinterpret_cast<char*>(boxes[g]) + kbuf_off) + (i64)gp * ld + base;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (base + j < ld) dst[j] = v[j];
+    }
+  }
+  // the column V[:, x*] of the incremental conditioning
+  if (V != nullptr && base < m_pad) {
+    double c[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j)
+      c[j] = (valid && base + j < m_pad) ? V[gp * v_stride_q + (base + j) * ldv + r] : 0.0;
+    for (int g = 0; g < G; ++g) {
+      double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(boxes[g]) + pcol_off) + (i64)gp * m_pad + base;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j)
+        if (base + j < m_pad) dst[j] = c[j];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int t = atomicAdd(&me->ticket, 1u);
+    s_last = (t == total - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if ((int)threadIdx.x < G) {
+    __threadfence_system();
+    if (threadIdx.x == 0) me->ticket = 0;
+    st_release_sys(&hdr(boxes[threadIdx.x])->row_seq, s);
+  }
+}
+
+// One thread: wait for the row of exchange row_step + 1, then advance.
+__global__ void peer_wait_row_kernel(void* mailbox, const i64* __restrict__ idx_dev, i64 idx_host,
+                                     const double* __restrict__ mean, i64 N, int q, double* __restrict__ scal) {
+  PeerHeader* h = hdr(mailbox);
+  const i64 idx = idx_dev ? *idx_dev : idx_host;
+  if ((int)threadIdx.x < q && idx >= 0 && idx < N) scal[threadIdx.x] = mean[(i64)threadIdx.x * N + idx];
+  if (threadIdx.x == 0) {
+    const unsigned long long s = h->row_step + 1;
+    if (!spin_until(&h->row_seq, s)) h->error = TAL_PEER_ERR_ROW_TIMEOUT;
+    h->row_step = s;
+  }
+}
+
+static i64 align_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
+
+}  // namespace tal
+
+using namespace tal;
+
+extern "C" {
+
+long long tal_peer_header_bytes(void) { return (long long)align_up(sizeof(PeerHeader), 256); }
+
+int tal_peer_alloc(long long bytes, void** ptr_host) {
+  TAL_ARG(bytes > 0 && ptr_host);
+  void* p = nullptr;
+  TAL_CUDA(cudaMalloc(&p, (size_t)bytes));
+  TAL_CUDA(cudaMemset(p, 0, (size_t)bytes));
+  TAL_CUDA(cudaDeviceSynchronize());
+  *ptr_host = p;
+  return TAL_OK;
+}
+
+int tal_peer_free(void* ptr) {
+  if (ptr) TAL_CUDA(cudaFree(ptr));
+  return TAL_OK;
+}
+
+int tal_peer_export(void* ptr, unsigned char* handle_host) {
+  TAL_ARG(ptr && handle_host);
+  static_assert(sizeof(cudaIpcMemHandle_t) == TAL_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  TAL_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_host, &h, sizeof(h));
+  return TAL_OK;
+}
+
+int tal_peer_import(const unsigned char* handle_host, void** ptr_host) {
+  TAL_ARG(handle_host && ptr_host);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  void* p = nullptr;
+  TAL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_host = p;
+  return TAL_OK;
+}
+
+int tal_peer_unimport(void* ptr) {
+  if (ptr) TAL_CUDA(cudaIpcCloseMemHandle(ptr));
+  return TAL_OK;
+}
+
+int tal_peer_enable_access(int peer_device) {
+  int dev = 0, can = 0;
+  TAL_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev) return TAL_OK;
+  TAL_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) {
+    tal::set_error("tal_peer_enable_access: device %d cannot access device %d", dev, peer_device);
+    return TAL_ERR_CUDA;
+  }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+    tal::set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+    return TAL_ERR_CUDA;
+  }
+  cudaGetLastError();
+  return TAL_OK;
+}
+
+int tal_peer_publish_record(const tal_argmax_result* rec, void* const* mailboxes, int G, int rank,
+                            void* stream) {
+  TAL_ARG(rec && mailboxes && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
+  peer_publish_kernel<<<1, 32, 0, as_stream(stream)>>>(rec, mailboxes, G, rank);
+  TAL_LAUNCH_CHECK("tal_peer_publish_record");
+  return TAL_OK;
+}
+
+int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void* stream) {
+  TAL_ARG(mailbox && out && G >= 1 && G <= kPeerMax);
+  peer_combine_kernel<<<1, 32, 0, as_stream(stream)>>>(mailbox, G, out);
+  TAL_LAUNCH_CHECK("tal_peer_combine_records");
+  return TAL_OK;
+}
+
+int tal_peer_push_row(void* const* mailboxes, int G, int rank, long long rows_per_rank, const void* cov,
+                      long long cov_stride_q, long long ld, long long row0, long long n_loc, int q,
+                      const long long* idx_dev, long long idx_host, long long kbuf_off,
+                      const double* V, long long v_stride_q, long long ldv, long long m_pad,
+                      long long pcol_off, int dtype, void* stream) {
+  TAL_ARG(mailboxes && cov && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= 1 && n_loc >= 0 && rows_per_rank >= 1);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(kbuf_off >= (long long)sizeof(PeerHeader) && kbuf_off % 16 == 0);
+  TAL_ARG(V == nullptr || (m_pad >= 1 && ldv >= n_loc && pcol_off % 16 == 0));
+  constexpr int EPT = 4;
+  const i64 span = V ? (ld > m_pad ? ld : m_pad) : ld;
+  dim3 grid((unsigned)((span + 256 * EPT - 1) / (256 * EPT)), q);
+  if (dtype == TAL_F64)
+    peer_push_row_kernel<double, EPT><<<grid, 256, 0, as_stream(stream)>>>(
+        mailboxes, G, rank, rows_per_rank, (const double*)cov, cov_stride_q, ld, row0, n_loc, idx_dev,
+        idx_host, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+  else
+    peer_push_row_kernel<float, EPT><<<grid, 256, 0, as_stream(stream)>>>(
+        mailboxes, G, rank, rows_per_rank, (const float*)cov, cov_stride_q, ld, row0, n_loc, idx_dev,
+        idx_host, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+  TAL_LAUNCH_CHECK("tal_peer_push_row");
+  return TAL_OK;
+}
+
+int tal_peer_wait_row(void* mailbox, const long long* idx_dev, long long idx_host, const double* mean,
+                      long long N, int q, double* scal, void* stream) {
+  TAL_ARG(mailbox && mean && scal && q >= 1 && q <= TAL_MAX_Q && N >= 1);
+  peer_wait_row_kernel<<<1, 32, 0, as_stream(stream)>>>(mailbox, idx_dev, idx_host, mean, N, q, scal);
+  TAL_LAUNCH_CHECK("tal_peer_wait_row");
+  return TAL_OK;
+}
+
+int tal_peer_error(const void* mailbox, int* error_host, void* stream) {
+  TAL_ARG(mailbox && error_host);
+  const PeerHeader* h = reinterpret_cast<const PeerHeader*>(mailbox);
+  TAL_CUDA(cudaMemcpyAsync(error_host, &h->error, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
+  TAL_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return TAL_OK;
+}
+
+}  // extern "C"

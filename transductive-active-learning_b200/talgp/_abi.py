@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtal_b200.so")
 # mirrors of the header's constants
 TAL_OK = 0
 TAL_MAX_Q = 16
+TAL_PEER_MAX = 16
+TAL_PEER_HANDLE_BYTES = 64
 F64, F32 = 0, 1
 KERNEL_GAUSSIAN, KERNEL_LAPLACE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(5)
 RULE_VTL, RULE_CTL, RULE_MMITL, RULE_TRUVAR = range(4)
@@ -82,6 +84,19 @@ SIGNATURES = {
     "tal_argmax_scratch_bytes": (_ll, []),
     "tal_masked_argmax": (_i, [_p, _p, _p, _i, _i, _ll, _p, _ll, _ll, _p, _p, _p]),
     "tal_argmax_combine": (_i, [_p, _i, _p, _p]),
+    "tal_peer_header_bytes": (_ll, []),
+    "tal_peer_alloc": (_i, [_ll, C.POINTER(_p)]),
+    "tal_peer_free": (_i, [_p]),
+    "tal_peer_export": (_i, [_p, C.c_char_p]),
+    "tal_peer_import": (_i, [C.c_char_p, C.POINTER(_p)]),
+    "tal_peer_unimport": (_i, [_p]),
+    "tal_peer_enable_access": (_i, [_i]),
+    "tal_peer_publish_record": (_i, [_p, _p, _i, _i, _p]),
+    "tal_peer_combine_records": (_i, [_p, _i, _p, _p]),
+    "tal_peer_push_row": (_i, [_p, _i, _i, _ll, _p, _ll, _ll, _ll, _ll, _i, _p, _ll, _ll, _p, _ll, _ll,
+                               _ll, _ll, _i, _p]),
+    "tal_peer_wait_row": (_i, [_p, _p, _ll, _p, _ll, _i, _p, _p]),
+    "tal_peer_error": (_i, [_p, C.POINTER(_i), _p]),
     "tal_probe_fp64": (_i, [_i, _i, _i, _p, _p]),
 }
 

@@ -133,12 +133,213 @@ class ThreadComm:
         sh["barrier"].wait()
 
 
+# ------------------------------------------------------ NVLink peer-memory exchange
+class _DevMem:
+    """A raw device allocation exposed through __cuda_array_interface__ so that
+    torch can alias it without owning it."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _view(ptr: int, shape, dtype: torch.dtype, device) -> torch.Tensor:
+    ts = {torch.float64: "<f8", torch.float32: "<f4", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+    return torch.as_tensor(_DevMem(ptr, shape, ts), device=device)
+
+
+class PeerViews:
+    def __init__(self, kbuf, pcol, kbuf_off, pcol_off, m_pad):
+        self.kbuf, self.pcol, self.kbuf_off, self.pcol_off, self.m_pad = kbuf, pcol, kbuf_off, pcol_off, m_pad
+
+
+class _PeerMixin:
+    """The per-step exchanges over NVLink peer memory (csrc/peer.cu): every rank
+    owns a mailbox, the peers map it (CUDA IPC between processes, plain pointers
+    between threads of one process), and the arg-max all-gather / observed-row
+    broadcast become P2P stores + release/acquire sequence numbers.  Set-up
+    collectives (handle exchange, Sigma_AA assembly) still use the base class."""
+    peer = True
+
+    def _peer_init(self):
+        from . import _abi
+        self.lib = _abi.load()
+        self._box = None        # own mailbox (device pointer, int)
+        self._peers = []        # mailbox pointers as seen from this rank
+        self._imported = []
+        self._table = None      # device array of the G pointers
+        self._layout = None
+
+    def _exchange_ptrs(self, own_ptr: int):
+        raise NotImplementedError
+
+    def _host_barrier(self):
+        raise NotImplementedError
+
+    def attach(self, q: int, ld: int, dtype: torch.dtype, m_pad: int, device) -> PeerViews:
+        """(Re)allocate the mailboxes for a [q, ld] row buffer and a [q, m_pad]
+        conditioning column.  Collective: every rank calls it at the same point."""
+        from . import _abi
+        lib = self.lib
+        if self.world > _abi.TAL_PEER_MAX:
+            raise ValueError("too many ranks for the peer mailbox")
+        item = 8 if dtype == torch.float64 else 4
+        up = lambda x: (x + 255) // 256 * 256  # noqa: E731
+        hb = int(lib.tal_peer_header_bytes())
+        kbuf_off = hb
+        pcol_off = kbuf_off + up(q * ld * item)
+        total = pcol_off + up(max(1, q * m_pad) * 8)
+        torch.cuda.synchronize(device)
+        self._host_barrier()
+        self.release()
+        box = C.c_void_p()
+        _abi.check(lib.tal_peer_alloc(total, C.byref(box)), "tal_peer_alloc")
+        self._box = int(box.value)
+        self._peers = self._exchange_ptrs(self._box)
+        self._table = torch.tensor(self._peers, dtype=torch.int64, device=device)
+        self._layout = (q, ld, dtype, m_pad)
+        torch.cuda.synchronize(device)
+        self._host_barrier()
+        kbuf = _view(self._box + kbuf_off, (q, ld), dtype, device)
+        pcol = _view(self._box + pcol_off, (q, max(1, m_pad)), torch.float64, device)
+        return PeerViews(kbuf, pcol, kbuf_off, pcol_off, m_pad)
+
+    def release(self):
+        from . import _abi
+        if self._box is None:
+            return
+        for p in self._imported:
+            _abi.check(self.lib.tal_peer_unimport(C.c_void_p(p)), "tal_peer_unimport")
+        self._imported = []
+        self._host_barrier()  # nobody maps this rank's mailbox any more
+        _abi.check(self.lib.tal_peer_free(C.c_void_p(self._box)), "tal_peer_free")
+        self._box, self._peers, self._table = None, [], None
+
+    @property
+    def table_ptr(self):
+        return C.c_void_p(self._table.data_ptr())
+
+    @property
+    def box_ptr(self):
+        return C.c_void_p(self._box)
+
+    def error(self) -> int:
+        from . import _abi
+        err = C.c_int(0)
+        _abi.check(self.lib.tal_peer_error(self.box_ptr, C.byref(err),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tal_peer_error")
+        return int(err.value)
+
+
+class PeerComm(_PeerMixin, NcclComm):
+    """One process per GPU (torchrun): NCCL for set-up, CUDA-IPC peer memory for
+    the per-step exchanges."""
+
+    def __init__(self, group=None):
+        NcclComm.__init__(self, group)
+        self._peer_init()
+
+    def _host_barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def _exchange_ptrs(self, own_ptr: int):
+        from . import _abi
+        h = C.create_string_buffer(_abi.TAL_PEER_HANDLE_BYTES)
+        _abi.check(self.lib.tal_peer_export(C.c_void_p(own_ptr), h), "tal_peer_export")
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(h.raw), group=self.group)
+        else:
+            handles = [bytes(h.raw)]
+        ptrs = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(own_ptr)
+                continue
+            p = C.c_void_p()
+            _abi.check(self.lib.tal_peer_import(hb, C.byref(p)), "tal_peer_import")
+            self._imported.append(int(p.value))
+            ptrs.append(int(p.value))
+        return ptrs
+
+
+class LocalPeerComm(_PeerMixin, ThreadComm):
+    """The same peer-memory protocol between `world` threads of ONE process that
+    drive one shard each on the same GPU, every thread on its OWN stream (the
+    kernels of different shards must run concurrently: they wait on each other).
+    Pointers are shared directly; used to test csrc/peer.cu on a single GPU."""
+
+    def __init__(self, shared: dict, rank: int, world: int):
+        ThreadComm.__init__(self, shared, rank, world)
+        self._peer_init()
+
+    def _host_barrier(self):
+        self.shared["barrier"].wait()
+
+    def _exchange_ptrs(self, own_ptr: int):
+        sh = self.shared
+        sh["slots"][self.rank] = own_ptr
+        sh["barrier"].wait()
+        ptrs = [int(sh["slots"][r]) for r in range(self.world)]
+        sh["barrier"].wait()
+        return ptrs
+
+    # ThreadComm's collectives rely on one shared stream (issue order = execution
+    # order); with one stream per thread every hand-over needs a stream sync.
+    def sum_(self, buf):
+        sh, st = self.shared, torch.cuda.current_stream()
+        st.synchronize()
+        sh["slots"][self.rank] = buf
+        sh["barrier"].wait()
+        tot = sh["slots"][0].clone()
+        for r in range(1, self.world):
+            tot += sh["slots"][r]
+        st.synchronize()
+        sh["barrier"].wait()  # every thread has finished reading
+        buf.copy_(tot)
+        st.synchronize()
+        sh["barrier"].wait()
+        return buf
+
+    def all_gather_(self, part, out):
+        sh, st = self.shared, torch.cuda.current_stream()
+        st.synchronize()
+        sh["slots"][self.rank] = part
+        sh["barrier"].wait()
+        n = part.numel()
+        for r in range(self.world):
+            out[r * n:(r + 1) * n].copy_(sh["slots"][r])
+        st.synchronize()
+        sh["barrier"].wait()
+
+    def gather_records(self, rec, out):
+        sh, st = self.shared, torch.cuda.current_stream()
+        st.synchronize()
+        sh["slots"][self.rank] = rec
+        sh["barrier"].wait()
+        for r in range(self.world):
+            out[r].copy_(sh["slots"][r])
+        st.synchronize()
+        sh["barrier"].wait()
+
+
 # ------------------------------------------------------------------ device side
 def ShardedGP(N: int, q: int, dtype=torch.float64, device=None, comm=None, rank1_variant: int = 0):
     """A DeviceGP holding this rank's row block (talgp.engine.DeviceGP with a communicator)."""
     from .engine import DeviceGP
     return DeviceGP(N, q, dtype=dtype, device=device, rank1_variant=rank1_variant,
-                    comm=comm if comm is not None else NcclComm())
+                    comm=comm if comm is not None else default_comm())
+
+
+def default_comm(group=None):
+    """PeerComm (NVLink peer-memory exchange) between the GPUs of one box when the
+    process group runs on NCCL; NcclComm otherwise or with TAL_EXCHANGE=nccl."""
+    import os
+    if (dist.is_initialized() and dist.get_backend(group) == "nccl"
+            and os.environ.get("TAL_EXCHANGE", "peer") != "nccl"):
+        return PeerComm(group)
+    return NcclComm(group)
 
 
 class ShardedITLBench:
@@ -172,38 +373,25 @@ class ShardedITLBench:
     def breakdown(self, steps: int = 10):
         """Per-phase device times of one step (CUDA events; diagnostic)."""
         gp = self.gp
-        names = ["score", "argmax_local", "gather+combine", "extract_row", "sum(kbuf)", "step_vectors",
-                 "cond_extract", "sum(pcol)", "cond_update", "rank1_update"]
+        names = ["score", "argmax_local", "combine_records", "exchange_row", "step_vectors",
+                 "cond_downdate", "rank1_update"]
         acc = np.zeros(len(names))
         for _ in range(steps):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
             ev[0].record()
             F = self.score(); ev[1].record()
-            sl = slice(gp.row0, gp.row0 + gp.n_loc)
             rec = gp.masked_argmax(F, None, 1, None, idx_offset=gp.row0, l_offset=gp.row0); ev[2].record()
             if gp.comm is not None:
-                from . import _abi
-                from .engine import _ptr, _stream
-                gp.comm.gather_records(rec, gp._recs)
-                _abi.check(gp.lib.tal_argmax_combine(_ptr(gp._recs), gp.comm.world, _ptr(gp._combined), _stream()))
+                gp.combine_records(rec)
                 rec = gp._combined
             ev[3].record()
             idx_dev = rec[0:1]
-            gp.extract_row(idx_dev); ev[4].record()
-            gp._sum(gp.kbuf); ev[5].record()
-            gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta); ev[6].record()
-            st = gp._cond
-            from . import _abi
-            from .engine import _ptr, _stream
-            _abi.check(gp.lib.tal_cond_extract_col(_ptr(st["V"][0]), st["ncols"], st["m_pad"], gp.row0, gp.n_loc,
-                                                   _ptr(idx_dev), 0, _ptr(st["pcol"]), _stream())); ev[7].record()
-            gp._sum(st["pcol"]); ev[8].record()
-            _abi.check(gp.lib.tal_cond_update(_ptr(st["V"][0]), st["ncols"], st["m_pad"], st["ncols"], gp.n_loc,
-                                              gp.row0, _ptr(st["pcol"]), _ptr(gp.kbuf[0]), _ptr(gp.wbuf[0]),
-                                              _ptr(gp.rho[0]), _ptr(idx_dev), 0, _ptr(st["coef"]),
-                                              _ptr(st["cs"][0]), int(gp.cond_chunks), _ptr(st["chunk"]),
-                                              gp.dt, _stream())); ev[9].record()
-            gp.rank1_update(); ev[10].record()
+            gp.exchange_row(idx_dev); ev[4].record()
+            gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta); ev[5].record()
+            if gp._cond is not None and gp._cond["valid"]:
+                gp._cond_downdate(idx_dev, 0)
+            ev[6].record()
+            gp.rank1_update(); ev[7].record()
             torch.cuda.synchronize()
             acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
         return dict(zip(names, (acc / steps * 1e3).round(1).tolist()))  # microseconds
@@ -212,8 +400,7 @@ class ShardedITLBench:
         rec = self._select()
         idx_dev = rec[0:1]
         gp = self.gp
-        gp.extract_row(idx_dev)
-        gp._sum(gp.kbuf)
+        gp.exchange_row(idx_dev)
         gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta)
         if gp._cond is not None and gp._cond["valid"]:
             gp._cond_downdate(idx_dev, 0)

@@ -101,13 +101,44 @@ class DeviceGP:
         self._ws = {}  # named scratch tensors, grown on demand
         self._cond = None  # incremental conditioning state (score_itl_directed)
         self.cond_chunks = 0  # tal_cond_update: 0 = choose, 1 = single pass, > 1 = row-parallel
+        self._peer = None  # NVLink peer-memory exchange state (talgp.dist.PeerViews)
         if self.comm is not None:
             self._recs = torch.zeros((self.comm.world, 4), dtype=torch.int64, device=dev)
             self._combined = torch.zeros((4,), dtype=torch.int64, device=dev)
+            if getattr(self.comm, "peer", False):
+                self._peer_attach(0)
 
     @property
     def sharded(self) -> bool:
         return self.comm is not None
+
+    def _peer_attach(self, m_pad: int) -> None:
+        """(Re)allocate the peer mailboxes; the observed-row buffer kbuf and the
+        conditioning column then live inside this rank's mailbox, where the
+        owner of the row stores them (csrc/peer.cu).  Collective."""
+        self._peer = self.comm.attach(self.q, self.ld, self.dtype, int(m_pad), self.device)
+        self.kbuf = self._peer.kbuf
+        from .dist import shard_rows
+        self._rows_per_rank = shard_rows(self.N, self.comm.world, 0)[1]
+
+    def exchange_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
+        """kbuf <- cov[:, idx, :] on every rank (the row lives on one shard) and
+        scal <- mean[:, idx]; in peer mode also pcol <- V[:, :, idx] when the
+        incremental conditioning is live."""
+        if self._peer is None:
+            self.extract_row(idx_dev, idx_host)
+            self._sum(self.kbuf)
+            return
+        st = self._cond if (self._cond is not None and self._cond["valid"]) else None
+        pv, comm = self._peer, self.comm
+        _abi.check(self.lib.tal_peer_push_row(
+            comm.table_ptr, comm.world, comm.rank, self._rows_per_rank, _ptr(self.cov), self.cov_stride_q,
+            self.ld, self.row0, self.n_loc, self.q, _ptr(idx_dev), int(idx_host), pv.kbuf_off,
+            _ptr(st["V"]) if st is not None else None,
+            st["m_pad"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
+            st["m_pad"] if st is not None else 0, pv.pcol_off, self.dt, _stream()), "tal_peer_push_row")
+        _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
+                                              self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
 
     def _sum(self, buf: torch.Tensor) -> None:
         """Complete a buffer that only its owner filled (sum = broadcast)."""
@@ -224,11 +255,11 @@ class DeviceGP:
             self._y_host.copy_(torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1)))
             self._y_dev.copy_(self._y_host, non_blocking=True)
             y_dev = self._y_dev
-        self.extract_row(idx_dev, idx_host)
         if allreduce is not None:
+            self.extract_row(idx_dev, idx_host)
             allreduce(self.kbuf)
         else:
-            self._sum(self.kbuf)
+            self.exchange_row(idx_dev, idx_host)
         self.step_vectors(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
         if self._cond is not None and self._cond["valid"]:
             self._cond_downdate(idx_dev, idx_host)
@@ -426,6 +457,8 @@ class DeviceGP:
                                             dtype=torch.float64, device=self.device))
             st.update(key=roi_key, m_pad=m_pad, ncols=ncols, valid=False)
             self._cond = st
+            if self._peer is not None and self._peer.m_pad < m_pad:
+                self._peer_attach(m_pad)
         if not incremental and st is not None:
             st["valid"] = False
         for i in range(self.q):
@@ -447,13 +480,17 @@ class DeviceGP:
         st = self._cond
         for i in range(self.q):
             V = st["V"][i]
-            _abi.check(self.lib.tal_cond_extract_col(
-                _ptr(V), st["ncols"], st["m_pad"], self.row0, self.n_loc, _ptr(idx_dev),
-                int(idx_host), _ptr(st["pcol"]), _stream()), "tal_cond_extract_col")
-            self._sum(st["pcol"])
+            if self._peer is not None:  # the owner stored V[i][:, x] with the row (exchange_row)
+                pcol = self._peer.pcol[i]
+            else:
+                pcol = st["pcol"]
+                _abi.check(self.lib.tal_cond_extract_col(
+                    _ptr(V), st["ncols"], st["m_pad"], self.row0, self.n_loc, _ptr(idx_dev),
+                    int(idx_host), _ptr(pcol), _stream()), "tal_cond_extract_col")
+                self._sum(pcol)
             _abi.check(self.lib.tal_cond_update(
                 _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_loc, self.row0,
-                _ptr(st["pcol"]), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
+                _ptr(pcol), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
                 _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]),
                 int(self.cond_chunks), _ptr(st["chunk"]), self.dt, _stream()), "tal_cond_update")
 
@@ -485,10 +522,21 @@ class DeviceGP:
         rec = self.masked_argmax(F_loc, safe[sl] if safe is not None else None, first_constraint,
                                  sample[sl] if sample is not None else None, idx_offset=self.row0,
                                  l_offset=self.row0)
-        self.comm.gather_records(rec, self._recs)
-        _abi.check(self.lib.tal_argmax_combine(_ptr(self._recs), self.comm.world,
-                                               _ptr(self._combined), _stream()), "tal_argmax_combine")
+        self.combine_records(rec)
         return self._combined
+
+    def combine_records(self, rec: torch.Tensor) -> None:
+        """_combined <- lexicographic reduce of every shard's arg-max record."""
+        comm = self.comm
+        if self._peer is not None:
+            _abi.check(self.lib.tal_peer_publish_record(_ptr(rec), comm.table_ptr, comm.world, comm.rank,
+                                                        _stream()), "tal_peer_publish_record")
+            _abi.check(self.lib.tal_peer_combine_records(comm.box_ptr, comm.world, _ptr(self._combined),
+                                                         _stream()), "tal_peer_combine_records")
+            return
+        comm.gather_records(rec, self._recs)
+        _abi.check(self.lib.tal_argmax_combine(_ptr(self._recs), comm.world,
+                                               _ptr(self._combined), _stream()), "tal_argmax_combine")
 
     def read_result(self, result: Optional[torch.Tensor] = None) -> _abi.ArgmaxResult:
         """Device -> host read of an arg-max record (synchronises the stream)."""
