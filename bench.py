@@ -189,7 +189,7 @@ def run_reference(args, w):
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / res["value"],
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, w, 1),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -199,6 +199,65 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def recompute_kernels(gp, roi, hbm_peak):
+    """Live timings (CUDA events) of the kernels of one full re-conditioning: TRSM and Cholesky against the
+    measured DMMA.8x8x4 fp64 tensor peak (tal_probe_fp64), the column-sum-of-squares pass against HBM."""
+    import ctypes as C
+    import torch
+    from talgp import _abi
+    lib = gp.lib
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    # fp64 tensor peak: 148*8 CTAs x 256 threads of independent DMMA chains
+    out = torch.zeros((1 << 20,), dtype=torch.float64, device=gp.device)
+    blocks, iters = 148 * 8, 4096
+    ms = timed(lambda: _abi.check(lib.tal_probe_fp64(0, blocks, iters, C.c_void_p(out.data_ptr()), stream)))
+    dmma_peak = blocks * iters * 16 * 8 * 512 / (ms * 1e-3) / 1e12
+    m_pad, ncols = gp._cond_dims(roi.m)
+    S = gp._scratch("cv_S", (m_pad, m_pad)); B = gp._scratch("cv_B", (m_pad, ncols))
+    work = gp._scratch("cv_work", (int(lib.tal_potrf_work_bytes(m_pad)) // 8,))
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def gather():
+        _abi.check(lib.tal_gather_roi(p(gp.cov[0]), gp.ld, gp.N, p(roi.idx), roi.m, m_pad, 1e-5, p(S), m_pad,
+                                      p(B), ncols, gp.dt, stream))
+    def potrf():
+        gather()
+        _abi.check(lib.tal_potrf_lower(p(S), m_pad, m_pad, p(work), stream))
+    def trsm():
+        _abi.check(lib.tal_trsm_lower(p(S), m_pad, m_pad, p(work), p(B), ncols, ncols, stream))
+    t_gather = timed(gather)
+    t_potrf = timed(potrf) - t_gather
+    gather(); potrf()
+    t_trsm = timed(trsm, reps=2)  # (solving in place repeatedly: same flops every time)
+    res = []
+    fl = float(m_pad) * m_pad * ncols
+    res.append({"kernel": "trsm_lower (L^-1 Sigma_AX, fp64 DMMA.8x8x4 mma.sync)", "bound": "tensor",
+                "achieved": fl / (t_trsm * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": fl / (t_trsm * 1e-3) / 1e12 / dmma_peak, "flops_per_launch": fl, "ms_per_launch": t_trsm,
+                "peak_source": "measured live: tal_probe_fp64 (independent DMMA.8x8x4 chains, all SMs)"})
+    fl = float(m_pad) ** 3 / 3
+    res.append({"kernel": "potrf_lower (blocked Cholesky of Sigma_AA + jitter^2 I)", "bound": "tensor",
+                "achieved": fl / (t_potrf * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+                "frac": fl / (t_potrf * 1e-3) / 1e12 / dmma_peak, "flops_per_launch": fl, "ms_per_launch": t_potrf,
+                "note": "latency-bound: serial chain of diagonal blocks"})
+    gb = 2.0 * roi.m * gp.ld * 8
+    res.append({"kernel": "gather_roi (Sigma[A, :] rows -> dense B, Sigma_AA)", "bound": "hbm",
+                "achieved": gb / (t_gather * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": gb / (t_gather * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": gb,
+                "ms_per_launch": t_gather})
+    return res
+
+
 def workload_config(args, w, world):
     return {
         "workload": (f"BASELINE configs[{4 if args.workload == 'c5' else 2}]: synthetic transductive ITL, "
@@ -206,10 +265,30 @@ def workload_config(args, w, world):
                      f"(l={w['lengthscale']}), q=1, rho={w['rho']}, fp64"),
         "name": args.workload, "N": w["N"], "m": w["m"], "d": w["d"], "q": 1,
         "conditioning": args.conditioning,
+        "storage": ("full N x N covariance (reference layout)" if args.storage == "full" else
+                    "lower-block: only the blocks on or below the diagonal are maintained (symmetric matrix)"),
         "l2": "inputs larger than L2 (covariance %.1f GB per GPU >> 126 MB): no flush needed"
               % (w["N"] * w["N"] * 8 / world / 1e9),
         "parallelism": "1 GPU" if world == 1 else f"covariance row-sharded over {world} GPUs",
     }
+
+
+def ncu_traffic(kernel_prefix, workload, n_gpus, storage="full"):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/*_kernel_traffic.json),
+    or None when no capture of this workload / GPU count is on file."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernel_traffic.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("workload") != workload or d.get("n_gpus") != n_gpus or d.get("storage", "full") != storage:
+            continue
+        for name, k in d.get("kernels", {}).items():
+            if name.startswith(kernel_prefix):
+                best = k["dram_bytes"]
+    return best
 
 
 # ----------------------------------------------------------------------- GPU arm
@@ -254,7 +333,8 @@ def run_ours(args, w):
         def build_model():
             nz = HomoscedasticNoise(1, np.array([rho]))
             distrs = prior_distr(nz, domain, np.zeros((0, w["d"])), np.zeros((1, 0)),
-                                 [stationary.Matern52(lengthscale=w["lengthscale"])], [ZeroMean()])
+                                 [stationary.Matern52(lengthscale=w["lengthscale"])], [ZeroMean()],
+                                 storage=args.storage)
             model = MarginalModel(0, domain, distrs, beta=np.array(beta), noise_rate=nz)
             alg = ITL(model, index_roi_constructor(A), conditioning=args.conditioning)
             alg.sample_mask()  # static; computed once (lib/algorithms/__init__.py:80)
@@ -267,7 +347,7 @@ def run_ours(args, w):
         inc = args.conditioning == "incremental"
 
         # ---- device-resident loop (value) -----------------------------------
-        ev = []
+        ev, ev_cond = [], []
 
         def dev_step(record):
             F = gp.score_itl_directed(roi.idx, roi.m, incremental=inc, roi_key=roi)
@@ -276,7 +356,14 @@ def run_ours(args, w):
             gp.extract_row(idx_dev)
             gp.step_vectors(idx_dev, 0, table_dev, N, True, beta)
             if gp._cond is not None and gp._cond["valid"]:
-                gp._cond_downdate(idx_dev, 0)
+                if record:
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    gp._cond_downdate(idx_dev, 0)
+                    c1.record()
+                    ev_cond.append((c0, c1))
+                else:
+                    gp._cond_downdate(idx_dev, 0)
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -333,23 +420,41 @@ def run_ours(args, w):
         d2h = 32 + 8 * w["d"] + 4  # arg-max record + selected point + subset-test flag
         value = args.steps / (total_ms / 1e3)
         e2e_value = e2e_steps / (e2e_ms / 1e3)
-        alg_bytes = 2.0 * model.q * N * gp.ld * 8
+        alg_bytes = gp.update_bytes()
         achieved = alg_bytes / (rank1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, w, 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-            "roofline": {"kernel": "rank1_update (tal_rank1_update)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": "rank1_update (tal_rank1_update%s)" % ("_lower" if args.storage == "lower" else ""),
+                         "bound": "hbm", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         "traffic": ncu_traffic("rank1_", args.workload, 1, args.storage),
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rank1_ms,
-                         "share_of_step": rank1_ms / (total_ms / args.steps)},
+                         "share_of_step": rank1_ms / (total_ms / args.steps),
+                         "frac_of_8TBs_datasheet": achieved / 8000.0},
         }
+        # the scoring pass of this mode next to the dominant kernel (north_star: HBM GB/s of the
+        # rank-1 update AND the scoring pass; tensor-pipe utilisation of the TRSM in recompute mode)
+        line["kernels"] = []
+        if ev_cond:
+            st = gp._cond
+            cond_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_cond]))
+            cbytes = 2.0 * model.q * st["m_pad"] * st["ncols"] * 8
+            line["kernels"].append({
+                "kernel": "cond_update (incremental target-set conditioning = the ITL scoring pass)",
+                "bound": "hbm", "achieved": cbytes / (cond_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": cbytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": cbytes,
+                "ms_per_launch": cond_ms, "traffic": ncu_traffic("cond_update", args.workload, 1, args.storage),
+                "share_of_step": cond_ms / (total_ms / args.steps)})
+        if not inc:
+            line["kernels"] += recompute_kernels(gp, roi, hbm_peak)
         # the recompute-every-step figure beside the incremental one (and vice versa)
         if args.both:
             other = "recompute" if inc else "incremental"
@@ -357,11 +462,11 @@ def run_ours(args, w):
             torch.cuda.empty_cache()
             sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(max(3, args.steps // 4)),
                                   "--warmup", "2", "--conditioning", other, "--workload", args.workload,
-                                  "--no-both", "--no-cpu"], capture_output=True, text=True)
+                                  "--storage", args.storage, "--no-both", "--no-cpu"], capture_output=True, text=True)
             try:
                 o = json.loads(sub.stdout.strip().splitlines()[-1])
                 line["value_" + other] = {"value": o["value"], "ms_per_step": o["ms_per_step"],
-                                          "e2e": o["e2e"]["value"]}
+                                          "e2e": o["e2e"]["value"], "kernels": o.get("kernels", [])}
             except Exception as exc:  # pragma: no cover
                 line["value_" + other] = {"error": str(exc), "stderr": sub.stderr[-300:]}
         if not args.no_cpu:
@@ -372,7 +477,7 @@ def run_ours(args, w):
 
     # ---- N > 1: row-sharded -------------------------------------------------
     from talgp.dist import ShardedITLBench
-    bench = ShardedITLBench(domain, A, table, w, world, rank, dev, args.conditioning)
+    bench = ShardedITLBench(domain, A, table, w, world, rank, dev, args.conditioning, storage=args.storage)
     for _ in range(args.warmup):
         bench.step(False)
     torch.cuda.synchronize()
@@ -401,11 +506,11 @@ def run_ours(args, w):
         assert err == 0, f"peer exchange timed out (TAL_PEER_ERR {err})"
     if os.environ.get("TAL_BREAKDOWN"):
         bd = bench.breakdown()
-        if rank == 0:
-            sys.stderr.write("breakdown_us " + json.dumps(bd) + "\n")
+        if rank in (0, world - 1):
+            sys.stderr.write(f"breakdown_us rank {rank} " + json.dumps(bd) + "\n")
     if rank == 0:
         total_ms, rank1_ms = float(total_ms), float(rank1_ms)
-        alg_bytes = 2.0 * bench.gp.n_loc * bench.gp.ld * 8
+        alg_bytes = bench.gp.update_bytes()
         achieved = alg_bytes / (rank1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
@@ -418,8 +523,10 @@ def run_ours(args, w):
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": {"kernel": "rank1_update (tal_rank1_update), per GPU, max over ranks", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                         "ms_per_launch": rank1_ms, "share_of_step": rank1_ms / (total_ms / args.steps)},
+                         "peak_source": peak_src, "traffic": ncu_traffic("rank1_", args.workload, world, args.storage),
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "ms_per_launch": rank1_ms, "share_of_step": rank1_ms / (total_ms / args.steps),
+                         "frac_of_8TBs_datasheet": achieved / 8000.0},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
@@ -434,6 +541,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--conditioning", default="incremental", choices=["incremental", "recompute"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--storage", default=os.environ.get("TAL_STORAGE", "full"), choices=["full", "lower"],
+                    help="covariance storage: full N x N (reference layout) or lower-block (symmetric)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-both", dest="both", action="store_false",

@@ -132,6 +132,39 @@ int tal_rank1_update(void* cov, long long cov_stride_q, long long ld, long long 
                      long long n_loc, long long N, int q, const void* kbuf, const void* wbuf,
                      int dtype, int variant, void* stream);
 
+/* ---- lower-block ("symmetric") storage -------------------------------------
+ * The posterior covariance is symmetric (up to the rounding of k_a w_b versus
+ * k_b w_a), so an opt-in storage mode maintains only the blocks on or below the
+ * diagonal: of global row g the columns [0, cend(g)), cend(g) = min(ld,
+ * (g / B + 1) * B), B = tal_sym_block(dtype) elements (8 KiB of a row).  Entry
+ * (g, c) with c >= cend(g) is read as (c, g).  The allocation and addressing are
+ * unchanged ([q][n_loc][ld]); the blocks above the diagonal are simply not
+ * touched, which halves the HBM traffic of the rank-1 update.
+ * tal_rank1_update_lower: as tal_rank1_update on the kept blocks only
+ *   (algorithmic bytes 2*q*s*sum_rows cend(row)); row0 must be a multiple of 32.
+ * tal_extract_row_lower / tal_gather_rows_lower: as tal_extract_row /
+ *   tal_gather_rows, assembling the row from the part this shard keeps
+ *   (zeros elsewhere, so that a sum over shards is the row).
+ * tal_rankm_update_lower: as tal_rankm_update on the kept blocks.
+ * tal_sym_mirror: one GPU holding all rows: fills the blocks above the diagonal
+ *   from their mirror images (before handing the matrix to a full-storage reader). */
+long long tal_sym_block(int dtype);
+int tal_rank1_update_lower(void* cov, long long cov_stride_q, long long ld, long long row0,
+                           long long n_loc, long long N, int q, const void* kbuf, const void* wbuf,
+                           int dtype, void* stream);
+int tal_extract_row_lower(const void* cov, long long cov_stride_q, long long ld, long long row0,
+                          long long n_loc, long long N, int q, const long long* idx_dev,
+                          long long idx_host, const double* mean, void* kbuf, double* scal, int dtype,
+                          void* stream);
+int tal_gather_rows_lower(const void* cov, long long ld, long long row0, long long n_loc, long long N,
+                          const long long* obs_idx, long long m, double* B, long long ldb, int dtype,
+                          void* stream);
+int tal_rankm_update_lower(void* cov, long long ld, long long row0, long long n_loc, long long N,
+                           const double* B, const double* W, long long ldb, int m, int dtype,
+                           void* stream);
+int tal_sym_mirror(void* cov, long long cov_stride_q, long long ld, long long N, int q, int dtype,
+                   void* stream);
+
 /* ---- posterior update, m observations ---------------------------------
  * Replaces GaussianDistribution.posterior for general m (prior_distr,
  * lib/gp/prior.py:52-66; SafeOpt/GoOSE replay).  One GP per call.
@@ -335,18 +368,23 @@ int tal_peer_enable_access(int peer_device);                    /* same-process 
 int tal_peer_publish_record(const tal_argmax_result* rec, void* const* mailboxes, int G, int rank,
                             void* stream);
 int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void* stream);
-/* broadcast of the observed row: the owner (idx / rows_per_rank) waits until
- * every rank has signalled that its row buffer is free, then stores
- * cov[:, idx - row0, :] into every mailbox's kbuf and, if V != null, the column
- * V[:, :, idx - row0] (V is [q][m_pad][ldv] fp64, the incremental-conditioning
- * state) into every mailbox's pcol; tal_peer_wait_row blocks the stream until the
- * data of this exchange has landed and writes scal[i] = mean[i][idx].           */
-int tal_peer_push_row(void* const* mailboxes, int G, int rank, long long rows_per_rank, const void* cov,
-                      long long cov_stride_q, long long ld, long long row0, long long n_loc, int q,
+/* broadcast of the observed row.  bounds_host[G+1]: rank g holds global rows
+ * [bounds[g], bounds[g+1]) (multiples of 4; bounds[G] = N).  Every rank signals
+ * every peer that its row buffer is free, stores the piece of row idx it holds
+ * into every mailbox's kbuf once that peer is ready, and signals completion;
+ * full storage: the owner of row idx holds the whole row; lower != 0 (lower-block
+ * storage, see tal_rank1_update_lower): the owner holds the columns below the
+ * diagonal block's end, the owners of the later rows hold the rest as their
+ * column idx.  If V != null the owner also stores the column V[:, :, idx - row0]
+ * (V is [q][m_pad][ldv] fp64, the incremental-conditioning state) into every
+ * mailbox's pcol.  tal_peer_wait_row blocks the stream until the G pieces of this
+ * exchange have landed and writes scal[i] = mean[i][idx].                       */
+int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* bounds_host, const void* cov,
+                      long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
                       long long pcol_off, int dtype, void* stream);
-int tal_peer_wait_row(void* mailbox, const long long* idx_dev, long long idx_host, const double* mean,
+int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,
                       long long N, int q, double* scal, void* stream);
 int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synchronises */
 

@@ -82,7 +82,7 @@ def build_oracle(p, rule=None):
     return model, alg, O.TableFunction(p["domain"], p["table"])
 
 
-def build_cuda(p, comm=None, rule=None, **alg_kw):
+def build_cuda(p, comm=None, rule=None, storage="full", **alg_kw):
     from lib.algorithms import index_roi_constructor, pe_roi_constructor, pm_roi_constructor
     from lib.algorithms.ctl import CTL
     from lib.algorithms.itl import ITL
@@ -97,7 +97,7 @@ def build_cuda(p, comm=None, rule=None, **alg_kw):
     q = len(p["kernels"])
     ks = [getattr(stationary, k)(variance=v, lengthscale=l) for k, v, l in p["kernels"]]
     noise = HomoscedasticNoise(q, np.asarray(p["rho"]))
-    distrs = prior_distr(noise, p["domain"], p["X0"], p["y0"], ks, [ZeroMean()] * q, comm=comm)
+    distrs = prior_distr(noise, p["domain"], p["X0"], p["y0"], ks, [ZeroMean()] * q, comm=comm, storage=storage)
     model = MarginalModel(0, p["domain"], distrs, beta=np.asarray(p["beta"], float), noise_rate=noise,
                           use_objective_as_constraint=p["fc_obj"])
     if isinstance(p["roi"], str):

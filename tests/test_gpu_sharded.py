@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="thread"):
+def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="thread", storage="full"):
     from talgp.dist import LocalPeerComm, ShardedITLBench, ThreadComm
     shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
     out = [None] * G
@@ -20,7 +20,7 @@ def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="th
 
     def body(rank):
         comm = ThreadComm(shared, rank, G) if exchange == "thread" else LocalPeerComm(shared, rank, G)
-        b = ShardedITLBench(domain, A, table, w, G, rank, cuda, conditioning, comm=comm)
+        b = ShardedITLBench(domain, A, table, w, G, rank, cuda, conditioning, comm=comm, storage=storage)
         sel, Fs = [], []
         for t in range(steps):
             F = b.score()
@@ -54,10 +54,11 @@ def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="th
     return out
 
 
+@pytest.mark.parametrize("storage", ["full", "lower"])
 @pytest.mark.parametrize("exchange", ["thread", "peer"])
 @pytest.mark.parametrize("conditioning", ["incremental", "recompute"])
 @pytest.mark.parametrize("G", [2, 3])
-def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange):
+def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange, storage):
     """exchange="thread": host-emulated collectives on one stream; "peer": the NVLink
     peer-memory protocol of csrc/peer.cu (mailboxes, P2P stores, release/acquire
     sequence numbers) between shards running concurrently on their own streams."""
@@ -66,11 +67,13 @@ def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange):
     from bench import make_problem
     from talgp import _abi
     from talgp.engine import DeviceGP
-    w = dict(N=700, m=90, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=6)
+    # lower-block storage: N spans three 1024-column blocks so that the shards hold pieces of a row
+    w = (dict(N=700, m=90, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=6) if storage == "full" else
+         dict(N=2500, m=150, d=4, lengthscale=0.25, rho=0.1, beta=1.0, grid=8))
     domain, A, table = make_problem(w)
     N, steps = w["N"], 8
     # single-GPU engine
-    gp = DeviceGP(N, 1, device=cuda)
+    gp = DeviceGP(N, 1, device=cuda, storage=storage)
     dom = torch.as_tensor(domain, device=cuda).contiguous()
     gp.build_gram(0, _abi.KERNEL_MATERN52, 1.0, w["lengthscale"], dom)
     gp.rho.fill_(w["rho"]); gp.init_bounds([1.0])
@@ -83,7 +86,7 @@ def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange):
         rec = gp.masked_argmax(F, None, 1, None)
         sel1.append(int(rec[0].item()))
         gp.observe(rec[0:1].clone(), tab, [1.0], y_gather=True, y_stride=N)
-    out = _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange)
+    out = _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange, storage)
     # every rank saw the same selections, equal to the single-GPU run
     for b, sel, Fs in out:
         assert sel == sel1
@@ -91,7 +94,13 @@ def test_sharded_itl_matches_single_gpu(cuda, G, conditioning, exchange):
         Fcat = torch.cat([out[r][2][t] for r in range(G)])
         torch.testing.assert_close(Fcat, F1[t], rtol=1e-7, atol=1e-10)
     rows = torch.cat([out[r][0].gp.cov[0] for r in range(G)])
-    assert torch.equal(rows, gp.cov[0])  # the shards' rows ARE the single-GPU matrix
+    if storage == "lower":  # only the blocks on or below the diagonal are maintained
+        blk = int(gp.lib.tal_sym_block(gp.dt))
+        r = torch.arange(N, device=cuda)
+        kept = torch.arange(gp.ld, device=cuda)[None, :] < torch.clamp((r // blk + 1) * blk, max=gp.ld)[:, None]
+        assert torch.equal(rows[kept], gp.cov[0][kept])
+    else:
+        assert torch.equal(rows, gp.cov[0])  # the shards' rows ARE the single-GPU matrix
     for r in range(G):
         g = out[r][0].gp
         assert torch.equal(g.mean, gp.mean) and torch.equal(g.var, gp.var)

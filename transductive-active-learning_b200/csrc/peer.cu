@@ -36,11 +36,12 @@ struct alignas(64) PeerSlot {
 struct alignas(256) PeerHeader {
   unsigned long long rec_step;  // arg-max exchanges completed by THIS rank
   unsigned long long row_step;  // row exchanges completed by THIS rank
-  unsigned long long row_seq;   // written by the owner: row exchange whose data has landed
+  unsigned long long pad1;
   unsigned int ticket;          // last-block election of the push kernel
   int error;                    // != 0: a spin timed out (TAL_PEER_ERR_*)
   unsigned long long pad0[4];
-  unsigned long long ready[kPeerMax];  // ready[g] = s: rank g may receive row exchange s
+  unsigned long long ready[kPeerMax];    // ready[g] = s: rank g may receive row exchange s
+  unsigned long long row_seq[kPeerMax];  // row_seq[g] = s: rank g's piece of exchange s has landed here
   PeerSlot slot[2][kPeerMax];
 };
 
@@ -58,13 +59,14 @@ __device__ __forceinline__ unsigned long long now_ns() {
   return t;
 }
 
-// spin until *p == want; false on timeout
+// spin until *p >= want (the counters only grow; a peer without a piece may already
+// have announced the next exchange); false on timeout
 __device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
-  if (ld_acquire_sys(p) == want) return true;
+  if (ld_acquire_sys(p) >= want) return true;
   const unsigned long long t0 = now_ns();
   for (;;) {
     for (int i = 0; i < 64; ++i)
-      if (ld_acquire_sys(p) == want) return true;
+      if (ld_acquire_sys(p) >= want) return true;
     if (now_ns() - t0 > kSpinTimeoutNs) return false;
     __nanosleep(100);
   }
@@ -135,89 +137,106 @@ __global__ void peer_combine_kernel(void* mailbox, int G, tal_argmax_result* __r
 }
 
 // ---- observed-row broadcast --------------------------------------------------
-// grid (ceil(max(ld, m_pad) / (256 * EPT)), q).  Every rank runs it; only the
-// owner of row idx moves data.
-template <typename T, int EPT>
+// Row x* of every GP is assembled in every mailbox's kbuf from the pieces the
+// shards hold.  Full storage: the owner of row x* holds all of it.  Lower-block
+// storage (sym_block > 0): the owner holds columns [0, cend(x*)), and the shard
+// that owns row c >= cend(x*) holds entry c as cov[c][x*].  Every rank
+//   1. tells every peer "my row buffer is free for exchange s"   (ready[rank] = s),
+//   2. stores its piece into every peer's kbuf once that peer is ready,
+//   3. tells every peer "my piece of exchange s has landed"       (row_seq[rank] = s);
+// tal_peer_wait_row then waits for the G row_seq entries.  The owner also stores
+// the column V[:, x*] of the incremental conditioning (pcol).
+// grid (ceil(max(ld / VN, m_pad) / 256), q, G): block z stores to ONE peer
+// (staggered by rank so that the links are loaded evenly), 16 bytes per thread.
+struct ShardBounds {
+  i64 b[kPeerMax + 1];  // rank g holds global rows [b[g], b[g + 1])
+};
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, i64 rows_per_rank,
-                     const T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
+peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBounds bounds,
+                     const T* __restrict__ cov, i64 stride_q, i64 ld, i64 N, i64 sym_block,
                      const i64* __restrict__ idx_dev, i64 idx_host,
                      i64 kbuf_off,  // byte offset of kbuf [q][ld] inside a mailbox
                      const double* __restrict__ V, i64 v_stride_q, i64 ldv, i64 m_pad,
                      i64 pcol_off) {  // byte offset of pcol [q][m_pad] inside a mailbox (V != null)
+  typedef typename Vec16<T>::type V16;
+  constexpr int VN = Vec16<T>::n;
   __shared__ bool s_last;
-  __shared__ int s_ok;
   const int gp = blockIdx.y;
-  const i64 idx = idx_dev ? *idx_dev : idx_host;
+  i64 idx = idx_dev ? *idx_dev : idx_host;
+  if (idx < 0 || idx >= N) idx = -1;  // failed arg-max: zeros are exchanged, the protocol keeps moving
   PeerHeader* me = hdr(boxes[rank]);
   const unsigned long long s = me->row_step + 1;
-  int owner = (int)(idx / rows_per_rank);
-  if (owner < 0 || owner >= G) owner = 0;  // invalid index (failed arg-max): keep the protocol moving
-  if (blockIdx.x == 0 && gp == 0 && threadIdx.x == 0)
-    st_release_sys(&hdr(boxes[owner])->ready[rank], s);  // my row buffer is free for exchange s
-  if (owner != rank) return;
-  // owner: wait until every rank is ready to receive
-  if (threadIdx.x < 32) {
-    bool ok = true;
-    if ((int)threadIdx.x < G) ok = spin_until(&me->ready[threadIdx.x], s);
-    ok = __all_sync(0xffffffffu, ok);
-    if (threadIdx.x == 0) s_ok = ok ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_ok && threadIdx.x == 0) me->error = TAL_PEER_ERR_READY_TIMEOUT;
-  const i64 r = idx - row0;
-  const bool valid = r >= 0 && r < n_loc;
-  const i64 base = ((i64)blockIdx.x * 256 + threadIdx.x) * EPT;
-  // the row Sigma[x*, :] of GP gp
+  if (blockIdx.x == 0 && gp == 0 && blockIdx.z == 0 && (int)threadIdx.x < G)
+    st_release_sys(&hdr(boxes[threadIdx.x])->ready[rank], s);
+  const i64 row0 = bounds.b[rank], n_loc = bounds.b[rank + 1] - row0;
+  const i64 row_end = rank == G - 1 ? ld : row0 + n_loc;  // pad columns belong to the last shard (zeros)
+  const bool own = idx >= row0 && idx < row0 + n_loc;
+  const i64 cend = idx < 0 ? ld : (sym_block > 0 ? ((idx / sym_block + 1) * sym_block < ld
+                                                        ? (idx / sym_block + 1) * sym_block : ld) : ld);
+  const bool zero_owner = idx < 0 && rank == 0;  // invalid index: rank 0 fills zeros
+  const int g = (rank + (int)blockIdx.z) % G;  // the peer this block stores to
+  const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;
+  const i64 base = t * VN;
+  bool mine = false;
+  V16 v;
+  memset(&v, 0, sizeof(v));
   if (base < ld) {
-    T v[EPT];
+    if (base < cend) {
+      mine = own || zero_owner;
+      if (own) v = *reinterpret_cast<const V16*>(cov + gp * stride_q + (idx - row0) * ld + base);
+    } else if (base >= row0 && base < row_end) {
+      mine = true;
+      T e[VN];
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) v[j] = (valid && base + j < ld) ? cov[gp * stride_q + r * ld + base + j] : T(0);
-    for (int g = 0; g < G; ++g) {
-      T* dst = reinterpret_cast<T*>(reinterpret_cast<char*>(boxes[g]) + kbuf_off) + (i64)gp * ld + base;
-#pragma unroll
-      for (int j = 0; j < EPT; ++j)
-        if (base + j < ld) dst[j] = v[j];
+      for (int j = 0; j < VN; ++j) {
+        const i64 c = base + j;
+        e[j] = c < N ? cov[gp * stride_q + (c - row0) * ld + idx] : T(0);
+      }
+      memcpy(&v, e, sizeof(v));
     }
   }
-  // the column V[:, x*] of the incremental conditioning
-  if (V != nullptr && base < m_pad) {
-    double c[EPT];
-#pragma unroll
-    for (int j = 0; j < EPT; ++j)
-      c[j] = (valid && base + j < m_pad) ? V[gp * v_stride_q + (base + j) * ldv + r] : 0.0;
-    for (int g = 0; g < G; ++g) {
-      double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(boxes[g]) + pcol_off) + (i64)gp * m_pad + base;
-#pragma unroll
-      for (int j = 0; j < EPT; ++j)
-        if (base + j < m_pad) dst[j] = c[j];
-    }
+  const bool col_mine = V != nullptr && t < m_pad && (own || zero_owner);
+  // any data for this peer in this block?  (uniform per block except at piece boundaries)
+  const int any = __syncthreads_or((mine || col_mine) ? 1 : 0);
+  if (any) {
+    if (threadIdx.x == 0 && !spin_until(&me->ready[g], s)) me->error = TAL_PEER_ERR_READY_TIMEOUT;
+    __syncthreads();
+    char* box = reinterpret_cast<char*>(boxes[g]);
+    if (mine) *reinterpret_cast<V16*>(reinterpret_cast<T*>(box + kbuf_off) + (i64)gp * ld + base) = v;
+    if (col_mine)
+      reinterpret_cast<double*>(box + pcol_off)[(i64)gp * m_pad + t] =
+          own ? V[gp * v_stride_q + t * ldv + (idx - row0)] : 0.0;
+    __threadfence_system();
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int total = gridDim.x * gridDim.y;
-    const unsigned int t = atomicAdd(&me->ticket, 1u);
-    s_last = (t == total - 1);
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int tk = atomicAdd(&me->ticket, 1u);
+    s_last = (tk == total - 1);
   }
   __syncthreads();
   if (!s_last) return;
   if ((int)threadIdx.x < G) {
     __threadfence_system();
     if (threadIdx.x == 0) me->ticket = 0;
-    st_release_sys(&hdr(boxes[threadIdx.x])->row_seq, s);
+    st_release_sys(&hdr(boxes[threadIdx.x])->row_seq[rank], s);
   }
 }
 
-// One thread: wait for the row of exchange row_step + 1, then advance.
-__global__ void peer_wait_row_kernel(void* mailbox, const i64* __restrict__ idx_dev, i64 idx_host,
+// One warp: wait for the G pieces of exchange row_step + 1, then advance.
+__global__ void peer_wait_row_kernel(void* mailbox, int G, const i64* __restrict__ idx_dev, i64 idx_host,
                                      const double* __restrict__ mean, i64 N, int q, double* __restrict__ scal) {
   PeerHeader* h = hdr(mailbox);
   const i64 idx = idx_dev ? *idx_dev : idx_host;
+  const unsigned long long s = h->row_step + 1;
+  bool ok = true;
+  if ((int)threadIdx.x < G) ok = spin_until(&h->row_seq[threadIdx.x], s);
+  ok = __all_sync(0xffffffffu, ok);
   if ((int)threadIdx.x < q && idx >= 0 && idx < N) scal[threadIdx.x] = mean[(i64)threadIdx.x * N + idx];
   if (threadIdx.x == 0) {
-    const unsigned long long s = h->row_step + 1;
-    if (!spin_until(&h->row_seq, s)) h->error = TAL_PEER_ERR_ROW_TIMEOUT;
+    if (!ok) h->error = TAL_PEER_ERR_ROW_TIMEOUT;
     h->row_step = s;
   }
 }
@@ -304,35 +323,41 @@ int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void*
   return TAL_OK;
 }
 
-int tal_peer_push_row(void* const* mailboxes, int G, int rank, long long rows_per_rank, const void* cov,
-                      long long cov_stride_q, long long ld, long long row0, long long n_loc, int q,
+int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* bounds_host, const void* cov,
+                      long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
                       long long pcol_off, int dtype, void* stream) {
-  TAL_ARG(mailboxes && cov && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
-  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= 1 && n_loc >= 0 && rows_per_rank >= 1);
+  TAL_ARG(mailboxes && cov && bounds_host && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= N && N >= 1 && ld % 4 == 0);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   TAL_ARG(kbuf_off >= (long long)sizeof(PeerHeader) && kbuf_off % 16 == 0);
-  TAL_ARG(V == nullptr || (m_pad >= 1 && ldv >= n_loc && pcol_off % 16 == 0));
-  constexpr int EPT = 4;
-  const i64 span = V ? (ld > m_pad ? ld : m_pad) : ld;
-  dim3 grid((unsigned)((span + 256 * EPT - 1) / (256 * EPT)), q);
+  TAL_ARG(V == nullptr || (m_pad >= 1 && pcol_off % 16 == 0));
+  ShardBounds bounds;
+  for (int g = 0; g <= kPeerMax; ++g) bounds.b[g] = g <= G ? bounds_host[g] : bounds_host[G];
+  TAL_ARG(bounds.b[0] == 0 && bounds.b[G] == N);
+  for (int g = 0; g < G; ++g) TAL_ARG(bounds.b[g] <= bounds.b[g + 1] && bounds.b[g] % 4 == 0);
+  const i64 vn = dtype == TAL_F64 ? 2 : 4;
+  const i64 blk = lower ? (dtype == TAL_F64 ? 1024 : 2048) : 0;
+  i64 span = (ld + vn - 1) / vn;
+  if (V && m_pad > span) span = m_pad;
+  dim3 grid((unsigned)((span + 255) / 256), q, G);
   if (dtype == TAL_F64)
-    peer_push_row_kernel<double, EPT><<<grid, 256, 0, as_stream(stream)>>>(
-        mailboxes, G, rank, rows_per_rank, (const double*)cov, cov_stride_q, ld, row0, n_loc, idx_dev,
-        idx_host, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+    peer_push_row_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+        mailboxes, G, rank, bounds, (const double*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
+        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
   else
-    peer_push_row_kernel<float, EPT><<<grid, 256, 0, as_stream(stream)>>>(
-        mailboxes, G, rank, rows_per_rank, (const float*)cov, cov_stride_q, ld, row0, n_loc, idx_dev,
-        idx_host, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+    peer_push_row_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+        mailboxes, G, rank, bounds, (const float*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
+        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
   TAL_LAUNCH_CHECK("tal_peer_push_row");
   return TAL_OK;
 }
 
-int tal_peer_wait_row(void* mailbox, const long long* idx_dev, long long idx_host, const double* mean,
+int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,
                       long long N, int q, double* scal, void* stream) {
-  TAL_ARG(mailbox && mean && scal && q >= 1 && q <= TAL_MAX_Q && N >= 1);
-  peer_wait_row_kernel<<<1, 32, 0, as_stream(stream)>>>(mailbox, idx_dev, idx_host, mean, N, q, scal);
+  TAL_ARG(mailbox && mean && scal && q >= 1 && q <= TAL_MAX_Q && N >= 1 && G >= 1 && G <= kPeerMax);
+  peer_wait_row_kernel<<<1, 32, 0, as_stream(stream)>>>(mailbox, G, idx_dev, idx_host, mean, N, q, scal);
   TAL_LAUNCH_CHECK("tal_peer_wait_row");
   return TAL_OK;
 }

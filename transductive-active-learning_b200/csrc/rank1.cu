@@ -10,6 +10,14 @@
 
 namespace tal {
 
+// Lower-block ("symmetric") storage: of global row g only the columns
+// [0, sym_cend(g)) are maintained; entry (g, c) with c >= sym_cend(g) is read as
+// (c, g).  sym_block is a multiple of the CTA tiles (rows and columns).
+__device__ __forceinline__ i64 sym_cend(i64 grow, i64 block, i64 ld) {
+  const i64 e = (grow / block + 1) * block;
+  return e < ld ? e : ld;
+}
+
 // --------------------------------------------------------------------------
 // Phase 1: copy the observed row (or zeros on a shard that does not own it).
 // --------------------------------------------------------------------------
@@ -29,6 +37,12 @@ extract_row_kernel(const T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i6
     kbuf[(i64)gp * ld + col] = v;
   }
   if (col == 0) scal[gp] = mean[(i64)gp * N + idx];
+}
+
+__global__ void stash_mean_kernel(const double* __restrict__ mean, i64 N, int q,
+                                  const i64* __restrict__ idx_dev, i64 idx_host, double* __restrict__ scal) {
+  const i64 idx = idx_dev ? *idx_dev : idx_host;
+  if ((int)threadIdx.x < q && idx >= 0 && idx < N) scal[threadIdx.x] = mean[(i64)threadIdx.x * N + idx];
 }
 
 // --------------------------------------------------------------------------
@@ -165,16 +179,22 @@ struct Vec32<float> {
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(256)
 rank1_ldg32_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
-                   const T* __restrict__ kbuf, const T* __restrict__ wbuf, int rows_per_cta) {
+                   const T* __restrict__ kbuf, const T* __restrict__ wbuf, int rows_per_cta,
+                   i64 sym_block) {
   typedef typename Vec32<T>::type V;
   constexpr int VN = Vec32<T>::n;
   const int gp = blockIdx.z;
-  const i64 col = ((i64)blockIdx.y * 256 + threadIdx.x) * VN;
+  // lower-block storage: column tile in x (fastest), row block in y
+  const i64 rb = sym_block > 0 ? blockIdx.y : blockIdx.x;
+  const i64 ct = sym_block > 0 ? blockIdx.x : blockIdx.y;
+  const i64 col = (ct * 256 + threadIdx.x) * VN;
   if (col >= ld) return;
+  const i64 r0 = rb * rows_per_cta;
+  // only the blocks on or below the diagonal are kept (the CTA's rows share one sym block)
+  if (sym_block > 0 && ct * 256 * VN >= sym_cend(row0 + r0, sym_block, ld)) return;
   T* C = cov + gp * stride_q + col;
   const T* k = kbuf + (i64)gp * ld + row0;
   V wv = *reinterpret_cast<const V*>(wbuf + (i64)gp * ld + col);
-  const i64 r0 = (i64)blockIdx.x * rows_per_cta;
   const i64 r1 = min(n_loc, r0 + (i64)rows_per_cta);
   for (i64 r = r0; r < r1; r += UNROLL) {
     V c[UNROLL];
@@ -352,6 +372,56 @@ gather_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N
   B[j * ldb + col] = v;
 }
 
+// Lower-block storage: row idx is assembled from the stored part of the row
+// (columns below sym_cend(idx), on the shard that owns the row) and from column idx
+// of the rows at or beyond sym_cend(idx) (on the shards that own those rows); what
+// this shard does not hold is written as zero, so a sum over shards is the row.
+// grid (ceil(ld / 256), m rows, q).
+template <typename T, typename O>
+__global__ void __launch_bounds__(256)
+gather_rows_sym_kernel(const T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, i64 N,
+                       i64 sym_block, const i64* __restrict__ idx_list, i64 idx_host,
+                       O* __restrict__ out, i64 ldo, i64 out_stride_q, i64 ncols_out) {
+  const int gp = blockIdx.z;
+  const i64 idx = idx_list ? idx_list[blockIdx.y] : idx_host;
+  const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols_out) return;
+  const T* C = cov + gp * stride_q;
+  T v = T(0);
+  if (idx >= 0 && idx < N && c < N) {
+    if (c < sym_cend(idx, sym_block, ld)) {
+      const i64 r = idx - row0;
+      if (r >= 0 && r < n_loc) v = C[r * ld + c];
+    } else {
+      const i64 r = c - row0;
+      if (r >= 0 && r < n_loc) v = C[r * ld + idx];
+    }
+  }
+  out[gp * out_stride_q + (i64)blockIdx.y * ldo + c] = O(v);
+}
+
+// Fill the blocks above the diagonal from their mirror images (one GPU, all rows):
+// cov[r][c] = cov[c][r] for c >= sym_cend(r).  32 x 32 tiles through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sym_mirror_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 N, i64 sym_block) {
+  __shared__ T tile[32][33];
+  const int gp = blockIdx.z;
+  const i64 tr = blockIdx.y, tc = blockIdx.x;  // destination tile (rows tr*32.., cols tc*32..)
+  if (tc * 32 < sym_cend(tr * 32, sym_block, ld)) return;  // kept block: nothing to do
+  T* C = cov + gp * stride_q;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const i64 r = tc * 32 + j, c = tr * 32 + tx;  // source (r, c) = mirror of the destination tile
+    tile[j][tx] = (r < N && c < N) ? C[r * ld + c] : T(0);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const i64 r = tr * 32 + j, c = tc * 32 + tx;
+    if (r < N && c < N) C[r * ld + c] = tile[tx][j];
+  }
+}
+
 // One CTA: S = B[:, obs] + D, Cholesky in shared memory; then every thread
 // solves its own columns.  m <= 64.
 constexpr int kSmallM = 64;
@@ -434,12 +504,13 @@ template <typename T, int UNROLL>
 __global__ void __launch_bounds__(256)
 rankm_update_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N,
                     const double* __restrict__ B, const double* __restrict__ W, i64 ldb, int m,
-                    int rows_per_cta) {
+                    int rows_per_cta, i64 sym_block) {
   const i64 col = (i64)blockIdx.y * 256 + threadIdx.x;
   if (col >= N) return;
+  const i64 r0 = (i64)blockIdx.x * rows_per_cta;
+  if (sym_block > 0 && (i64)blockIdx.y * 256 >= sym_cend(row0 + r0, sym_block, ld)) return;
   double w[kSmallM];
   for (int j = 0; j < m; ++j) w[j] = W[(i64)j * ldb + col];
-  const i64 r0 = (i64)blockIdx.x * rows_per_cta;
   const i64 r1 = min(n_loc, r0 + (i64)rows_per_cta);
   for (i64 r = r0; r < r1; ++r) {
     double acc = 0.0;
@@ -503,9 +574,9 @@ int tal_step_vectors(const void* kbuf, void* wbuf, long long N, int q, const lon
 
 template <typename T>
 static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* kbuf,
-                        const T* wbuf, int variant, cudaStream_t st) {
+                        const T* wbuf, int variant, cudaStream_t st, i64 sym_block = 0) {
   if (n_loc == 0) return TAL_OK;
-  if (variant == 0) variant = 3;
+  if (variant == 0 || sym_block > 0) variant = 3;
   if (variant == 1) {
     constexpr int VN = Vec16<T>::n;
     const int rows_per_cta = 64;
@@ -516,10 +587,15 @@ static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
   } else if (variant == 3) {
     constexpr int VN = Vec32<T>::n;
     const int rows_per_cta = 32;
-    dim3 grid((unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta),
-              (unsigned)((ld + 256 * VN - 1) / (256 * VN)), q);
+    const unsigned row_blocks = (unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta);
+    const unsigned col_tiles = (unsigned)((ld + 256 * VN - 1) / (256 * VN));
+    if (sym_block > 0) {
+      TAL_ARG(sym_block % (256 * VN) == 0 && sym_block % rows_per_cta == 0 && row0 % rows_per_cta == 0);
+      TAL_ARG(row_blocks <= 65535);
+    }
+    dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
     rank1_ldg32_kernel<T, 4><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, kbuf, wbuf,
-                                                   rows_per_cta);
+                                                   rows_per_cta, sym_block);
   } else if (variant == 2) {
     constexpr int SEG = 8192, STAGES = 6, THREADS = 256;
     constexpr int SEG_ELEMS = SEG / (int)sizeof(T);
@@ -612,11 +688,104 @@ int tal_rankm_update(void* cov, long long ld, long long row0, long long n_loc, l
   dim3 grid((unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta), (unsigned)((N + 255) / 256));
   if (dtype == TAL_F64)
     rankm_update_kernel<double, 1><<<grid, 256, 0, as_stream(stream)>>>(
-        (double*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta);
+        (double*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta, 0);
   else
     rankm_update_kernel<float, 1><<<grid, 256, 0, as_stream(stream)>>>(
-        (float*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta);
+        (float*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta, 0);
   TAL_LAUNCH_CHECK("tal_rankm_update");
+  return TAL_OK;
+}
+
+/* ---- lower-block ("symmetric") storage ------------------------------------ */
+long long tal_sym_block(int dtype) { return dtype == TAL_F64 ? 1024 : 2048; }
+
+int tal_rank1_update_lower(void* cov, long long cov_stride_q, long long ld, long long row0,
+                           long long n_loc, long long N, int q, const void* kbuf, const void* wbuf,
+                           int dtype, void* stream) {
+  TAL_ARG(cov && kbuf && wbuf);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld == (N + 31) / 32 * 32 && n_loc >= 0);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  const i64 blk = tal_sym_block(dtype);
+  if (dtype == TAL_F64)
+    return launch_rank1<double>((double*)cov, cov_stride_q, ld, row0, n_loc, q, (const double*)kbuf,
+                                (const double*)wbuf, 3, as_stream(stream), blk);
+  return launch_rank1<float>((float*)cov, cov_stride_q, ld, row0, n_loc, q, (const float*)kbuf,
+                             (const float*)wbuf, 3, as_stream(stream), blk);
+}
+
+int tal_extract_row_lower(const void* cov, long long cov_stride_q, long long ld, long long row0,
+                          long long n_loc, long long N, int q, const long long* idx_dev,
+                          long long idx_host, const double* mean, void* kbuf, double* scal, int dtype,
+                          void* stream) {
+  TAL_ARG(cov && kbuf && scal && mean);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld >= N && n_loc >= 0);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  const i64 blk = tal_sym_block(dtype);
+  dim3 grid((unsigned)((ld + 255) / 256), 1, q);
+  if (dtype == TAL_F64)
+    gather_rows_sym_kernel<double, double><<<grid, 256, 0, as_stream(stream)>>>(
+        (const double*)cov, cov_stride_q, ld, row0, n_loc, N, blk, idx_dev, idx_host, (double*)kbuf, ld,
+        ld, ld);
+  else
+    gather_rows_sym_kernel<float, float><<<grid, 256, 0, as_stream(stream)>>>(
+        (const float*)cov, cov_stride_q, ld, row0, n_loc, N, blk, idx_dev, idx_host, (float*)kbuf, ld, ld,
+        ld);
+  TAL_LAUNCH_CHECK("tal_extract_row_lower");
+  stash_mean_kernel<<<1, 32, 0, as_stream(stream)>>>(mean, N, q, idx_dev, idx_host, scal);
+  TAL_LAUNCH_CHECK("tal_extract_row_lower/scal");
+  return TAL_OK;
+}
+
+int tal_gather_rows_lower(const void* cov, long long ld, long long row0, long long n_loc, long long N,
+                          const long long* obs_idx, long long m, double* B, long long ldb, int dtype,
+                          void* stream) {
+  TAL_ARG(cov && obs_idx && B && m >= 0 && ldb >= N);
+  if (m == 0) return TAL_OK;
+  TAL_ARG(m <= 65535);
+  const i64 blk = tal_sym_block(dtype);
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)m, 1);
+  if (dtype == TAL_F64)
+    gather_rows_sym_kernel<double, double><<<grid, 256, 0, as_stream(stream)>>>(
+        (const double*)cov, 0, ld, row0, n_loc, N, blk, obs_idx, 0, B, ldb, 0, N);
+  else
+    gather_rows_sym_kernel<float, double><<<grid, 256, 0, as_stream(stream)>>>(
+        (const float*)cov, 0, ld, row0, n_loc, N, blk, obs_idx, 0, B, ldb, 0, N);
+  TAL_LAUNCH_CHECK("tal_gather_rows_lower");
+  return TAL_OK;
+}
+
+int tal_rankm_update_lower(void* cov, long long ld, long long row0, long long n_loc, long long N,
+                           const double* B, const double* W, long long ldb, int m, int dtype,
+                           void* stream) {
+  TAL_ARG(cov && B && W && m >= 1 && m <= kSmallM);
+  if (n_loc == 0) return TAL_OK;
+  const int rows_per_cta = 32;
+  const i64 blk = tal_sym_block(dtype);
+  TAL_ARG(row0 % rows_per_cta == 0);
+  dim3 grid((unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta), (unsigned)((N + 255) / 256));
+  if (dtype == TAL_F64)
+    rankm_update_kernel<double, 1><<<grid, 256, 0, as_stream(stream)>>>(
+        (double*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta, blk);
+  else
+    rankm_update_kernel<float, 1><<<grid, 256, 0, as_stream(stream)>>>(
+        (float*)cov, ld, row0, n_loc, N, B, W, ldb, m, rows_per_cta, blk);
+  TAL_LAUNCH_CHECK("tal_rankm_update_lower");
+  return TAL_OK;
+}
+
+int tal_sym_mirror(void* cov, long long cov_stride_q, long long ld, long long N, int q, int dtype,
+                   void* stream) {
+  TAL_ARG(cov && q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld >= N);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  const i64 blk = tal_sym_block(dtype);
+  const unsigned t = (unsigned)((N + 31) / 32);
+  TAL_ARG(t <= 65535);
+  dim3 grid(t, t, q);
+  if (dtype == TAL_F64)
+    sym_mirror_kernel<double><<<grid, 256, 0, as_stream(stream)>>>((double*)cov, cov_stride_q, ld, N, blk);
+  else
+    sym_mirror_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)cov, cov_stride_q, ld, N, blk);
+  TAL_LAUNCH_CHECK("tal_sym_mirror");
   return TAL_OK;
 }
 

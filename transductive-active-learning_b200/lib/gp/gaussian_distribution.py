@@ -20,12 +20,12 @@ DEFAULT_JITTER = 1e-5  # gaussian_distribution.py:13
 
 
 class GaussianDistribution:
-    def __init__(self, mean, covariance, dtype: Optional[torch.dtype] = None):
+    def __init__(self, mean, covariance, dtype: Optional[torch.dtype] = None, storage: str = "full"):
         mean = as_f64(mean).reshape(-1)
         n = mean.shape[0]
         cov = covariance if isinstance(covariance, torch.Tensor) else as_f64(covariance)
         dtype = dtype or (cov.dtype if cov.dtype in (torch.float32, torch.float64) else torch.float64)
-        gp = DeviceGP(n, 1, dtype=dtype, device=mean.device)
+        gp = DeviceGP(n, 1, dtype=dtype, device=mean.device, storage=storage)
         gp.load_covariance(0, cov)
         gp.mean[0].copy_(mean)
         self._gp, self._slot = gp, 0
@@ -37,10 +37,10 @@ class GaussianDistribution:
         return self
 
     @classmethod
-    def initialize(cls, mean, kernel, X, dtype: torch.dtype = torch.float64):
+    def initialize(cls, mean, kernel, X, dtype: torch.dtype = torch.float64, storage: str = "full"):
         """:69-71 — the Gram matrix is built in place on the device."""
         X = as_f64(X)
-        gp = DeviceGP(X.shape[0], 1, dtype=dtype, device=X.device)
+        gp = DeviceGP(X.shape[0], 1, dtype=dtype, device=X.device, storage=storage)
         variance, lengthscale = kernel._gram_params()
         gp.build_gram(0, kernel.kind, variance, lengthscale, X)
         gp.mean[0].copy_(mean.vector(X))
@@ -69,7 +69,8 @@ class GaussianDistribution:
 
     def _clone(self) -> "GaussianDistribution":
         src = self._gp
-        gp = DeviceGP(src.N, 1, dtype=src.dtype, device=src.device)
+        src.ensure_full()
+        gp = DeviceGP(src.N, 1, dtype=src.dtype, device=src.device, storage=src.storage)
         gp.cov[0].copy_(src.cov[self._slot])
         gp.mean[0].copy_(src.mean[self._slot])
         gp.var[0].copy_(src.var[self._slot])

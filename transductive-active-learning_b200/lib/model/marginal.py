@@ -93,8 +93,9 @@ class MarginalModel(Model):
         if shared:
             self._gp = gp0  # adopt: built in one allocation by prior_distr
         else:  # jnp.array([distr.covariance ...]) (:47-48): one copy into a [q, n, ld] block
-            gp = DeviceGP(n, q, dtype=gp0.dtype, device=self.domain.device)
+            gp = DeviceGP(n, q, dtype=gp0.dtype, device=self.domain.device, storage=gp0.storage)
             for i, d in enumerate(distrs):
+                d._gp.ensure_full()
                 gp.cov[i].copy_(d._gp.cov[d._slot])
                 gp.mean[i].copy_(d._gp.mean[d._slot])
                 gp.var[i].copy_(d._gp.var[d._slot])
@@ -151,7 +152,7 @@ class MarginalModel(Model):
     def covariances(self) -> torch.Tensor:
         """[q, n, n] view of the HBM-resident covariances (row-sharded model:
         this rank's rows [q, n_loc, n], see `row_range`)."""
-        return self._gp.cov[:, :, : self.n]
+        return self._gp.covariances_view()
 
     @property
     def row_range(self):

@@ -28,19 +28,33 @@ import torch.distributed as dist
 
 
 # ------------------------------------------------------------------ host logic
-def shard_rows(N: int, world: int, rank: int, align: int = 64) -> Tuple[int, int]:
-    """Contiguous row block of `rank`: (row0, n_loc); blocks are multiples of
-    `align` rows except the last one."""
+def shard_bounds(N: int, world: int, align: int = 64, storage: str = "full") -> List[int]:
+    """Row boundaries b[0..world]: rank g holds global rows [b[g], b[g+1]).
+    full storage: equal blocks (multiples of `align` rows except the last);
+    lower-block storage: the kept part of row r is ~r columns long, so the
+    boundaries sit at N sqrt(g / world) to balance the update traffic."""
+    if storage == "lower":
+        b = [min(N, int(round(N * np.sqrt(g / world) / align)) * align) for g in range(world)] + [N]
+        for g in range(1, world + 1):
+            b[g] = max(b[g], b[g - 1])
+        return b
     per = -(-N // world)
     per = -(-per // align) * align
-    row0 = min(N, rank * per)
-    return row0, max(0, min(N, row0 + per) - row0)
+    return [min(N, g * per) for g in range(world)] + [N]
 
 
-def owner_of(N: int, world: int, idx: int, align: int = 64) -> int:
-    per = -(-N // world)
-    per = -(-per // align) * align
-    return int(idx) // per
+def shard_rows(N: int, world: int, rank: int, align: int = 64, storage: str = "full") -> Tuple[int, int]:
+    """Contiguous row block of `rank`: (row0, n_loc)."""
+    b = shard_bounds(N, world, align, storage)
+    return b[rank], b[rank + 1] - b[rank]
+
+
+def owner_of(N: int, world: int, idx: int, align: int = 64, storage: str = "full") -> int:
+    b = shard_bounds(N, world, align, storage)
+    for g in range(world):
+        if b[g] <= int(idx) < b[g + 1]:
+            return g
+    raise IndexError(idx)
 
 
 def sum_broadcast(buf: torch.Tensor, group=None) -> torch.Tensor:
@@ -325,11 +339,12 @@ class LocalPeerComm(_PeerMixin, ThreadComm):
 
 
 # ------------------------------------------------------------------ device side
-def ShardedGP(N: int, q: int, dtype=torch.float64, device=None, comm=None, rank1_variant: int = 0):
+def ShardedGP(N: int, q: int, dtype=torch.float64, device=None, comm=None, rank1_variant: int = 0,
+              storage: str = "full"):
     """A DeviceGP holding this rank's row block (talgp.engine.DeviceGP with a communicator)."""
     from .engine import DeviceGP
     return DeviceGP(N, q, dtype=dtype, device=device, rank1_variant=rank1_variant,
-                    comm=comm if comm is not None else default_comm())
+                    comm=comm if comm is not None else default_comm(), storage=storage)
 
 
 def default_comm(group=None):
@@ -345,11 +360,12 @@ def default_comm(group=None):
 class ShardedITLBench:
     """BASELINE config 3 row-sharded over the ranks: what bench.py times at --gpus > 1."""
 
-    def __init__(self, domain, A, table, w, world, rank, dev, conditioning="incremental", comm=None):
+    def __init__(self, domain, A, table, w, world, rank, dev, conditioning="incremental", comm=None,
+                 storage="full"):
         from . import _abi
         self.w = w
         N = w["N"]
-        self.gp = ShardedGP(N, 1, dtype=torch.float64, device=dev, comm=comm)
+        self.gp = ShardedGP(N, 1, dtype=torch.float64, device=dev, comm=comm, storage=storage)
         dom = torch.as_tensor(domain, device=dev).contiguous()
         self.gp.build_gram(0, _abi.KERNEL_MATERN52, 1.0, w["lengthscale"], dom)
         self.gp.rho.fill_(w["rho"])

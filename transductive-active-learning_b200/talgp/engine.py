@@ -59,15 +59,28 @@ def nearest_index(domain: torch.Tensor, A: torch.Tensor) -> torch.Tensor:
 class DeviceGP:
     def __init__(self, N: int, q: int, dtype: torch.dtype = torch.float64,
                  device: Optional[torch.device] = None, row0: int = 0,
-                 n_loc: Optional[int] = None, rank1_variant: int = 0, comm=None):
+                 n_loc: Optional[int] = None, rank1_variant: int = 0, comm=None,
+                 storage: str = "full"):
         """comm: None (one GPU) or a communicator of talgp.dist (NcclComm /
         ThreadComm): the covariance is then row-sharded over comm.world ranks and
-        this object holds rank comm.rank's block."""
+        this object holds rank comm.rank's block.
+        storage: "full" keeps every entry of the N x N matrices like the reference;
+        "lower" maintains only the blocks on or below the diagonal (the matrix is
+        symmetric), which halves the HBM traffic of every posterior update; readers
+        of full rows are served through the mirrored entries (include/tal_b200.h,
+        "lower-block storage")."""
         _abi.require_device()
+        if storage not in ("full", "lower"):
+            raise ValueError("storage must be 'full' or 'lower'")
+        self.storage, self.lower = storage, storage == "lower"
+        self._upper_stale = False
         self.comm = comm if (comm is not None and comm.world > 1) else None
+        from .dist import shard_bounds
         if self.comm is not None:
-            from .dist import shard_rows
-            row0, n_loc = shard_rows(int(N), comm.world, comm.rank)
+            self.bounds = shard_bounds(int(N), comm.world, storage=storage)
+            row0, n_loc = self.bounds[comm.rank], self.bounds[comm.rank + 1] - self.bounds[comm.rank]
+        else:
+            self.bounds = [0, int(N)]
         self.lib = _abi.load()
         if q < 1 or q > _abi.TAL_MAX_Q:
             raise ValueError(f"q must be in [1, {_abi.TAL_MAX_Q}]")
@@ -118,8 +131,7 @@ class DeviceGP:
         owner of the row stores them (csrc/peer.cu).  Collective."""
         self._peer = self.comm.attach(self.q, self.ld, self.dtype, int(m_pad), self.device)
         self.kbuf = self._peer.kbuf
-        from .dist import shard_rows
-        self._rows_per_rank = shard_rows(self.N, self.comm.world, 0)[1]
+        self._bounds_c = (C.c_longlong * len(self.bounds))(*self.bounds)
 
     def exchange_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
         """kbuf <- cov[:, idx, :] on every rank (the row lives on one shard) and
@@ -132,12 +144,12 @@ class DeviceGP:
         st = self._cond if (self._cond is not None and self._cond["valid"]) else None
         pv, comm = self._peer, self.comm
         _abi.check(self.lib.tal_peer_push_row(
-            comm.table_ptr, comm.world, comm.rank, self._rows_per_rank, _ptr(self.cov), self.cov_stride_q,
-            self.ld, self.row0, self.n_loc, self.q, _ptr(idx_dev), int(idx_host), pv.kbuf_off,
+            comm.table_ptr, comm.world, comm.rank, self._bounds_c, _ptr(self.cov), self.cov_stride_q,
+            self.ld, self.N, self.q, int(self.lower), _ptr(idx_dev), int(idx_host), pv.kbuf_off,
             _ptr(st["V"]) if st is not None else None,
             st["m_pad"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
             st["m_pad"] if st is not None else 0, pv.pcol_off, self.dt, _stream()), "tal_peer_push_row")
-        _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
+        _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, comm.world, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
                                               self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
 
     def _sum(self, buf: torch.Tensor) -> None:
@@ -149,13 +161,15 @@ class DeviceGP:
         """[n_loc] per-shard candidate vector -> [N] on every rank."""
         if self.comm is None:
             return F_loc
-        from .dist import shard_rows
-        per = shard_rows(self.N, self.comm.world, 0)[1]
+        b, G = self.bounds, self.comm.world
+        per = max(b[g + 1] - b[g] for g in range(G))
         pad = torch.zeros((per,), dtype=F_loc.dtype, device=self.device)
         pad[: self.n_loc] = F_loc
-        out = torch.empty((self.comm.world * per,), dtype=F_loc.dtype, device=self.device)
+        out = torch.empty((G * per,), dtype=F_loc.dtype, device=self.device)
         self.comm.all_gather_(pad, out)
-        return out[: self.N]
+        if all(b[g + 1] - b[g] == per for g in range(G - 1)):
+            return out[: self.N]
+        return torch.cat([out[g * per: g * per + b[g + 1] - b[g]] for g in range(G)])
 
     # ------------------------------------------------------------------ util
     def _scratch(self, name: str, shape, dtype=torch.float64) -> torch.Tensor:
@@ -172,7 +186,37 @@ class DeviceGP:
 
     def covariance_view(self, i: int) -> torch.Tensor:
         """[n_loc, N] view of GP i's covariance rows (no copy)."""
+        self.ensure_full()
         return self.cov[i, :, : self.N]
+
+    def covariances_view(self) -> torch.Tensor:
+        """[q, n_loc, N] view of all covariance rows (no copy)."""
+        self.ensure_full()
+        return self.cov[:, :, : self.N]
+
+    def ensure_full(self) -> None:
+        """Lower-block storage: make the blocks above the diagonal valid again
+        (mirror of the kept blocks) before a reader of full rows runs."""
+        if not (self.lower and self._upper_stale):
+            return
+        if self.comm is not None:
+            raise NotImplementedError("this operation reads full covariance rows; a row-sharded model in "
+                                      "lower-block storage holds the mirror images on other ranks")
+        _abi.check(self.lib.tal_sym_mirror(_ptr(self.cov), self.cov_stride_q, self.ld, self.N, self.q,
+                                           self.dt, _stream()), "tal_sym_mirror")
+        self._upper_stale = False
+
+    def update_bytes(self) -> float:
+        """Algorithmic HBM bytes of one posterior update of this shard (read + write
+        of every maintained covariance entry): 2 q n_loc ld s in full storage,
+        2 q s sum_rows cend(row) in lower-block storage."""
+        s = 8 if self.dtype == torch.float64 else 4
+        if not self.lower:
+            return 2.0 * self.q * self.n_loc * self.ld * s
+        blk = int(self.lib.tal_sym_block(self.dt))
+        r = np.arange(self.row0, self.row0 + self.n_loc, dtype=np.int64)
+        cend = np.minimum((r // blk + 1) * blk, self.ld)
+        return 2.0 * self.q * s * float(cend.sum())
 
     def launch_count(self) -> int:
         return int(self.lib.tal_launch_count())
@@ -185,6 +229,10 @@ class DeviceGP:
         assert domain.dtype == torch.float64 and domain.is_contiguous()
         n, d = domain.shape
         assert n == self.N
+        if self.q == 1:
+            self._upper_stale = False
+        else:
+            self.ensure_full()
         _abi.check(self.lib.tal_gram_stationary(
             kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
             _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
@@ -204,6 +252,10 @@ class DeviceGP:
     def load_covariance(self, i: int, cov) -> None:
         """Upload a full N x N covariance (host or device) into shard i."""
         src = torch.as_tensor(cov)
+        if self.q > 1:
+            self.ensure_full()
+        else:
+            self._upper_stale = False
         rows = src[self.row0:self.row0 + self.n_loc]
         self.cov[i, :, : self.N].copy_(rows.to(device=self.device, dtype=self.dtype))
         self.var[i].copy_(torch.diagonal(src).to(device=self.device, dtype=torch.float64))
@@ -219,7 +271,8 @@ class DeviceGP:
 
     # ------------------------------------------------------------------ update
     def extract_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
-        _abi.check(self.lib.tal_extract_row(
+        fn = self.lib.tal_extract_row_lower if self.lower else self.lib.tal_extract_row
+        _abi.check(fn(
             _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(idx_dev), int(idx_host), _ptr(self.mean), _ptr(self.kbuf), _ptr(self.scal),
             self.dt, _stream()), "tal_extract_row")
@@ -234,6 +287,12 @@ class DeviceGP:
             "tal_step_vectors")
 
     def rank1_update(self, variant: Optional[int] = None) -> None:
+        if self.lower:
+            self._upper_stale = True
+            _abi.check(self.lib.tal_rank1_update_lower(
+                _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+                _ptr(self.kbuf), _ptr(self.wbuf), self.dt, _stream()), "tal_rank1_update_lower")
+            return
         _abi.check(self.lib.tal_rank1_update(
             _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(self.kbuf), _ptr(self.wbuf), self.dt,
@@ -287,7 +346,8 @@ class DeviceGP:
             B = self._scratch("cond_B", (m, ldb))
             W = self._scratch("cond_W", (m, ldb))
             oi = obs_idx[s:e]
-            _abi.check(self.lib.tal_gather_rows(
+            gather = self.lib.tal_gather_rows_lower if self.lower else self.lib.tal_gather_rows
+            _abi.check(gather(
                 _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(oi), m, _ptr(B),
                 ldb, self.dt, _stream()), "tal_gather_rows")
             if allreduce is not None:
@@ -299,9 +359,12 @@ class DeviceGP:
                 _ptr(noise_std[s:e]) if noise_std is not None else None, float(jitter),
                 _ptr(y[s:e]), _ptr(W), _ptr(self.mean[i]), _ptr(self.var[i]), _stream()),
                 "tal_small_posterior_weights")
-            _abi.check(self.lib.tal_rankm_update(
+            update = self.lib.tal_rankm_update_lower if self.lower else self.lib.tal_rankm_update
+            _abi.check(update(
                 _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(B), _ptr(W), ldb,
                 m, self.dt, _stream()), "tal_rankm_update")
+            if self.lower:
+                self._upper_stale = True
         if self.dtype != torch.float64:
             self.var[i].copy_(self.var[i].to(self.dtype).to(torch.float64))
 
@@ -349,6 +412,7 @@ class DeviceGP:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
         lib = self.lib
         N = self.N
+        self.ensure_full()  # the row / column gathers below read entries on both sides of the diagonal
         sharded_cols = sharded_cols or self.sharded
         n_out = self.n_loc if sharded_cols else N
         off = self.row0 if sharded_cols else 0
@@ -411,7 +475,10 @@ class DeviceGP:
         S = self._scratch("cv_S", (m_pad, m_pad))
         B = self._scratch("cv_B", (m_pad, ldb)) if V is None else V
         work = self._scratch("cv_work", (int(lib.tal_potrf_work_bytes(m_pad)) // 8,))
-        if self.comm is None:
+        if self.lower and self.comm is not None:
+            self._gather_roi_lower_sharded(i, roi_idx, m, m_pad, ncols, jitter, S, B)
+        elif self.comm is None:
+            self.ensure_full()
             _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m,
                                           m_pad, float(jitter), _ptr(S), m_pad, _ptr(B), ldb,
                                           self.dt, _stream()), "tal_gather_roi")
@@ -432,6 +499,26 @@ class DeviceGP:
         _abi.check(lib.tal_colsumsq_dense(_ptr(B), ldb, m_pad, ncols, _ptr(part), n_split,
                                           _ptr(cs), _stream()), "tal_colsumsq_dense")
         return cs[: self.n_loc]
+
+    def _gather_roi_lower_sharded(self, i, roi_idx, m, m_pad, ncols, jitter, S, B) -> None:
+        """Sigma_AA (+ jitter^2 I, identity pad) into S and Sigma[A, own candidates] into B for a
+        row-sharded model in lower-block storage: the rows of the target set are assembled
+        64 at a time by the symmetric row gather + a sum over the shards (one-off per ROI)."""
+        S.zero_()
+        B.zero_()
+        rows = self._scratch("cv_rows", (64, self.ld))
+        idx = roi_idx[:m].contiguous()
+        for j0 in range(0, m, 64):
+            j1 = min(m, j0 + 64)
+            _abi.check(self.lib.tal_gather_rows_lower(
+                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(idx[j0:j1]), j1 - j0,
+                _ptr(rows), self.ld, self.dt, _stream()), "tal_gather_rows_lower")
+            self._sum(rows)
+            B[j0:j1, : self.n_loc] = rows[: j1 - j0, self.row0: self.row0 + self.n_loc]
+            S[j0:j1, :m] = rows[: j1 - j0].index_select(1, idx)
+        d = torch.arange(m_pad, device=self.device)
+        S[d[:m], d[:m]] += float(jitter) ** 2
+        S[d[m:], d[m:]] = 1.0
 
     def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
                            incremental: bool = False, roi_key=None) -> torch.Tensor:
