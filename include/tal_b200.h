@@ -375,15 +375,16 @@ int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void*
  * full storage: the owner of row idx holds the whole row; lower != 0 (lower-block
  * storage, see tal_rank1_update_lower): the owner holds the columns below the
  * diagonal block's end, the owners of the later rows hold the rest as their
- * column idx.  If V != null the owner also stores the column V[:, :, idx - row0]
- * (V is [q][m_pad][ldv] fp64, the incremental-conditioning state) into every
- * mailbox's pcol.  tal_peer_wait_row blocks the stream until the G pieces of this
+ * column idx.  If V != null (V is [q][m_pad][ldv] fp64, the incremental-
+ * conditioning state of candidates [cand0, cand0 + n_cand)) the rank whose
+ * candidate range contains idx also stores the column V[:, :, idx - cand0] into
+ * every mailbox's pcol.  tal_peer_wait_row blocks the stream until the G pieces of this
  * exchange have landed and writes scal[i] = mean[i][idx].                       */
 int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* bounds_host, const void* cov,
                       long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
-                      long long pcol_off, int dtype, void* stream);
+                      long long pcol_off, long long cand0, long long n_cand, int dtype, void* stream);
 int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,
                       long long N, int q, double* scal, void* stream);
 int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synchronises */

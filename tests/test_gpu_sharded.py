@@ -134,15 +134,18 @@ def test_sharded_vtl_columns_match_rows(cuda):
     torch.testing.assert_close(torch.cat(parts), F, rtol=1e-10, atol=0)
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
-def test_drop_in_api_row_sharded(cuda, name):
+@pytest.mark.parametrize("name,storage", [("c1", "full"), ("c2", "full"), ("c3", "full"), ("c4", "full"),
+                                          ("c1", "lower"), ("c3", "lower")])
+def test_drop_in_api_row_sharded(cuda, name, storage):
     """The `lib.*` classes over a row-sharded model (3 ranks emulated by threads):
-    same selections, scores and posterior as the single-GPU model."""
+    same selections, scores and posterior as the single-GPU model.  (Lower-block
+    storage: the ITL rules; the VTL-type rules read full rows and need full storage
+    on a sharded model.)"""
     import problems
     from talgp.dist import ThreadComm
     p = problems.ALL[name]()
     T = min(p["T"], 8)
-    m1, a1, f1 = problems.build_cuda(p)
+    m1, a1, f1 = problems.build_cuda(p, storage=storage)
     ref = []
     for t in range(T):
         r = a1.step(f1)
@@ -154,7 +157,7 @@ def test_drop_in_api_row_sharded(cuda, name):
     def worker(rank):
         try:
             torch.cuda.set_device(cuda)
-            m, a, f = problems.build_cuda(p, comm=ThreadComm(shared, rank, G))
+            m, a, f = problems.build_cuda(p, comm=ThreadComm(shared, rank, G), storage=storage)
             got = []
             for t in range(T):
                 r = a.step(f)
@@ -179,4 +182,12 @@ def test_drop_in_api_row_sharded(cuda, name):
         torch.testing.assert_close(m.means, m1.means, rtol=1e-10, atol=1e-13)
         torch.testing.assert_close(m.variances, m1.variances, rtol=1e-10, atol=1e-13)
         row0, n_loc = m.row_range
-        torch.testing.assert_close(m.covariances, m1.covariances[:, row0:row0 + n_loc], rtol=1e-10, atol=1e-13)
+        if storage == "full":
+            torch.testing.assert_close(m.covariances, m1.covariances[:, row0:row0 + n_loc], rtol=1e-10, atol=1e-13)
+        else:  # the kept blocks (the sharded model cannot mirror: the images live on other ranks)
+            with pytest.raises(NotImplementedError):
+                m.covariances
+            full = m1.covariances[:, row0:row0 + n_loc]
+            mine = m._gp.cov[:, :, : m.n]
+            low = torch.tril(torch.ones((m.n, m.n), dtype=torch.bool, device=cuda))[row0:row0 + n_loc]
+            torch.testing.assert_close(mine[:, low], full[:, low], rtol=1e-10, atol=1e-13)

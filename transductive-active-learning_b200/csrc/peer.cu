@@ -159,7 +159,8 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
                      const i64* __restrict__ idx_dev, i64 idx_host,
                      i64 kbuf_off,  // byte offset of kbuf [q][ld] inside a mailbox
                      const double* __restrict__ V, i64 v_stride_q, i64 ldv, i64 m_pad,
-                     i64 pcol_off) {  // byte offset of pcol [q][m_pad] inside a mailbox (V != null)
+                     i64 pcol_off,  // byte offset of pcol [q][m_pad] inside a mailbox (V != null)
+                     i64 cand0, i64 n_cand) {  // V holds columns (candidates) [cand0, cand0 + n_cand)
   typedef typename Vec16<T>::type V16;
   constexpr int VN = Vec16<T>::n;
   __shared__ bool s_last;
@@ -197,7 +198,8 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
       memcpy(&v, e, sizeof(v));
     }
   }
-  const bool col_mine = V != nullptr && t < m_pad && (own || zero_owner);
+  const bool own_col = idx >= cand0 && idx < cand0 + n_cand;
+  const bool col_mine = V != nullptr && t < m_pad && (own_col || zero_owner);
   // any data for this peer in this block?  (uniform per block except at piece boundaries)
   const int any = __syncthreads_or((mine || col_mine) ? 1 : 0);
   if (any) {
@@ -207,7 +209,7 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
     if (mine) *reinterpret_cast<V16*>(reinterpret_cast<T*>(box + kbuf_off) + (i64)gp * ld + base) = v;
     if (col_mine)
       reinterpret_cast<double*>(box + pcol_off)[(i64)gp * m_pad + t] =
-          own ? V[gp * v_stride_q + t * ldv + (idx - row0)] : 0.0;
+          own_col ? V[gp * v_stride_q + t * ldv + (idx - cand0)] : 0.0;
     __threadfence_system();
   }
   __syncthreads();
@@ -327,7 +329,7 @@ int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* 
                       long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
-                      long long pcol_off, int dtype, void* stream) {
+                      long long pcol_off, long long cand0, long long n_cand, int dtype, void* stream) {
   TAL_ARG(mailboxes && cov && bounds_host && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
   TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= N && N >= 1 && ld % 4 == 0);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
@@ -345,11 +347,11 @@ int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* 
   if (dtype == TAL_F64)
     peer_push_row_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
         mailboxes, G, rank, bounds, (const double*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
-        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, cand0, n_cand);
   else
     peer_push_row_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
         mailboxes, G, rank, bounds, (const float*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
-        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off);
+        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, cand0, n_cand);
   TAL_LAUNCH_CHECK("tal_peer_push_row");
   return TAL_OK;
 }

@@ -30,7 +30,7 @@ def _undirected(model: MarginalModel) -> torch.Tensor:
     """:28-30 — sum_i log(1 + var_i / rho_i^2)."""
     gp = model._gp
     F = gp.score_itl_undirected()
-    return F[gp.row0: gp.row0 + gp.n_loc] if gp.sharded else F
+    return F[gp.cand0: gp.cand0 + gp.n_cand] if gp.sharded else F
 
 
 def _directed(model: MarginalModel, roi, incremental: bool = False) -> torch.Tensor:

@@ -272,7 +272,7 @@ class MarginalModel(Model):
             safe = self.operating_safe_set.view(torch.uint8)
         gp = self._gp
         if gp.sharded and F.numel() == self.n:  # a full-length objective: this rank's candidates
-            F = F[gp.row0: gp.row0 + gp.n_loc]
+            F = F[gp.cand0: gp.cand0 + gp.n_cand]
         res = gp.read_result(gp.argmax_candidates(F, safe, self.first_constraint, sample_mask))
         self.last_argmax = res
         if res.status != _abi.ARGMAX_OK:

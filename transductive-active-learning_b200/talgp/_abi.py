@@ -94,7 +94,7 @@ SIGNATURES = {
     "tal_peer_publish_record": (_i, [_p, _p, _i, _i, _p]),
     "tal_peer_combine_records": (_i, [_p, _i, _p, _p]),
     "tal_peer_push_row": (_i, [_p, _i, _i, C.POINTER(_ll), _p, _ll, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _ll,
-                               _ll, _ll, _ll, _i, _p]),
+                               _ll, _ll, _ll, _ll, _ll, _i, _p]),
     "tal_peer_wait_row": (_i, [_p, _i, _p, _ll, _p, _ll, _i, _p, _p]),
     "tal_sym_block": (_ll, [_i]),
     "tal_rank1_update_lower": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _i, _p]),

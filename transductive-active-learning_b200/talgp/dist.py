@@ -396,7 +396,7 @@ class ShardedITLBench:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
             ev[0].record()
             F = self.score(); ev[1].record()
-            rec = gp.masked_argmax(F, None, 1, None, idx_offset=gp.row0, l_offset=gp.row0); ev[2].record()
+            rec = gp.masked_argmax(F, None, 1, None, idx_offset=gp.cand0, l_offset=gp.cand0); ev[2].record()
             if gp.comm is not None:
                 gp.combine_records(rec)
                 rec = gp._combined

@@ -92,6 +92,16 @@ class DeviceGP:
             "cuda", torch.cuda.current_device())
         self.row0 = int(row0)
         self.n_loc = self.N if n_loc is None else int(n_loc)
+        # candidates this rank scores (and holds conditioning state for): its own rows, except
+        # in lower-block storage, where the rows are split by AREA and the candidates evenly
+        self.cand_bounds = self.bounds
+        if self.comm is not None and self.lower:
+            self.cand_bounds = shard_bounds(self.N, comm.world, storage="full")
+        if self.comm is not None:
+            self.cand0 = self.cand_bounds[comm.rank]
+            self.n_cand = self.cand_bounds[comm.rank + 1] - self.cand0
+        else:
+            self.cand0, self.n_cand = self.row0, self.n_loc
         self.ld = round_up(self.N, 32)
         self.rank1_variant = rank1_variant
         dev = self.device
@@ -148,7 +158,8 @@ class DeviceGP:
             self.ld, self.N, self.q, int(self.lower), _ptr(idx_dev), int(idx_host), pv.kbuf_off,
             _ptr(st["V"]) if st is not None else None,
             st["m_pad"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
-            st["m_pad"] if st is not None else 0, pv.pcol_off, self.dt, _stream()), "tal_peer_push_row")
+            st["m_pad"] if st is not None else 0, pv.pcol_off, self.cand0, self.n_cand, self.dt, _stream()),
+            "tal_peer_push_row")
         _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, comm.world, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
                                               self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
 
@@ -158,13 +169,13 @@ class DeviceGP:
             self.comm.sum_(buf)
 
     def gather_candidates(self, F_loc: torch.Tensor) -> torch.Tensor:
-        """[n_loc] per-shard candidate vector -> [N] on every rank."""
+        """[n_cand] per-shard candidate vector -> [N] on every rank."""
         if self.comm is None:
             return F_loc
-        b, G = self.bounds, self.comm.world
+        b, G = self.cand_bounds, self.comm.world
         per = max(b[g + 1] - b[g] for g in range(G))
         pad = torch.zeros((per,), dtype=F_loc.dtype, device=self.device)
-        pad[: self.n_loc] = F_loc
+        pad[: self.n_cand] = F_loc
         out = torch.empty((G * per,), dtype=F_loc.dtype, device=self.device)
         self.comm.all_gather_(pad, out)
         if all(b[g + 1] - b[g] == per for g in range(G - 1)):
@@ -458,7 +469,7 @@ class DeviceGP:
         return F
 
     def _cond_dims(self, m: int):
-        return round_up(m, 128), round_up(max(self.n_loc, 1), 64)
+        return round_up(m, 128), round_up(max(self.n_cand, 1), 64)
 
     def cond_var_sumsq(self, i: int, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
                        V: Optional[torch.Tensor] = None,
@@ -498,7 +509,7 @@ class DeviceGP:
             cs = self._scratch("cv_cs", (ncols,))
         _abi.check(lib.tal_colsumsq_dense(_ptr(B), ldb, m_pad, ncols, _ptr(part), n_split,
                                           _ptr(cs), _stream()), "tal_colsumsq_dense")
-        return cs[: self.n_loc]
+        return cs[: self.n_cand]
 
     def _gather_roi_lower_sharded(self, i, roi_idx, m, m_pad, ncols, jitter, S, B) -> None:
         """Sigma_AA (+ jitter^2 I, identity pad) into S and Sigma[A, own candidates] into B for a
@@ -514,7 +525,7 @@ class DeviceGP:
                 _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(idx[j0:j1]), j1 - j0,
                 _ptr(rows), self.ld, self.dt, _stream()), "tal_gather_rows_lower")
             self._sum(rows)
-            B[j0:j1, : self.n_loc] = rows[: j1 - j0, self.row0: self.row0 + self.n_loc]
+            B[j0:j1, : self.n_cand] = rows[: j1 - j0, self.cand0: self.cand0 + self.n_cand]
             S[j0:j1, :m] = rows[: j1 - j0].index_select(1, idx)
         d = torch.arange(m_pad, device=self.device)
         S[d[:m], d[:m]] += float(jitter) ** 2
@@ -523,11 +534,11 @@ class DeviceGP:
     def score_itl_directed(self, roi_idx: torch.Tensor, m: int, jitter: float = 1e-5,
                            incremental: bool = False, roi_key=None) -> torch.Tensor:
         """sum_i 0.5 max(log((var_i + rho_i^2)/(var_i - cs_i + rho_i^2)), 0) (itl.py:50-58)
-        over this shard's candidates ([N] on one GPU, [n_loc] when row-sharded).
+        over this shard's candidates ([N] on one GPU, [n_cand] when row-sharded).
         incremental: keep V_i = L^-1 cov_i[A, :] resident and let `observe`
         downdate it (csrc/condinc.cu) as long as `roi_key` stays the same; the
         full Cholesky + TRSM then only runs when the ROI changes."""
-        n_out, off = self.n_loc, self.row0
+        n_out, off = self.n_cand, self.cand0
         F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
         st = self._cond
         reuse = incremental and st is not None and st["key"] is roi_key and st["valid"]
@@ -572,11 +583,11 @@ class DeviceGP:
             else:
                 pcol = st["pcol"]
                 _abi.check(self.lib.tal_cond_extract_col(
-                    _ptr(V), st["ncols"], st["m_pad"], self.row0, self.n_loc, _ptr(idx_dev),
+                    _ptr(V), st["ncols"], st["m_pad"], self.cand0, self.n_cand, _ptr(idx_dev),
                     int(idx_host), _ptr(pcol), _stream()), "tal_cond_extract_col")
                 self._sum(pcol)
             _abi.check(self.lib.tal_cond_update(
-                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_loc, self.row0,
+                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_cand, self.cand0,
                 _ptr(pcol), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
                 _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]),
                 int(self.cond_chunks), _ptr(st["chunk"]), self.dt, _stream()), "tal_cond_update")
@@ -605,10 +616,10 @@ class DeviceGP:
         the device record (int64[4]; [0] is the global index)."""
         if self.comm is None:
             return self.masked_argmax(F_loc, safe, first_constraint, sample)
-        sl = slice(self.row0, self.row0 + self.n_loc)
+        sl = slice(self.cand0, self.cand0 + self.n_cand)
         rec = self.masked_argmax(F_loc, safe[sl] if safe is not None else None, first_constraint,
-                                 sample[sl] if sample is not None else None, idx_offset=self.row0,
-                                 l_offset=self.row0)
+                                 sample[sl] if sample is not None else None, idx_offset=self.cand0,
+                                 l_offset=self.cand0)
         self.combine_records(rec)
         return self._combined
 
