@@ -438,7 +438,8 @@ def run_ours(args, w):
                          "traffic": ncu_traffic("rank1_", args.workload, 1, args.storage),
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rank1_ms,
                          "share_of_step": rank1_ms / (total_ms / args.steps),
-                         "frac_of_8TBs_datasheet": achieved / 8000.0},
+                         "frac_of_8TBs_datasheet": achieved / 8000.0,
+                         "effective_GBs_vs_full_matrix_bytes": 2.0 * model.q * N * N * 8 / (rank1_ms * 1e-3) / 1e9},
         }
         # the scoring pass of this mode next to the dominant kernel (north_star: HBM GB/s of the
         # rank-1 update AND the scoring pass; tensor-pipe utilisation of the TRSM in recompute mode)
@@ -446,29 +447,46 @@ def run_ours(args, w):
         if ev_cond:
             st = gp._cond
             cond_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_cond]))
-            cbytes = 2.0 * model.q * st["m_pad"] * st["ncols"] * 8
+            if st["append"]:  # one read of the factor (rows in use, mid-run) + two appended rows
+                cbytes = model.q * (st["rows"] - args.steps + 2.0) * st["ncols"] * 8
+                kname = "cond_append_update (incremental target-set conditioning = the ITL scoring pass; read-only GEMV over the factor)"
+            else:
+                cbytes = 2.0 * model.q * st["m_pad"] * st["ncols"] * 8
+                kname = "cond_update (incremental target-set conditioning = the ITL scoring pass; rewrites V)"
             line["kernels"].append({
-                "kernel": "cond_update (incremental target-set conditioning = the ITL scoring pass)",
+                "kernel": kname,
                 "bound": "hbm", "achieved": cbytes / (cond_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": cbytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": cbytes,
-                "ms_per_launch": cond_ms, "traffic": ncu_traffic("cond_update", args.workload, 1, args.storage),
+                "ms_per_launch": cond_ms, "traffic": ncu_traffic("cond_app_partial" if st["append"] else "cond_update", args.workload, 1, args.storage),
                 "share_of_step": cond_ms / (total_ms / args.steps)})
         if not inc:
             line["kernels"] += recompute_kernels(gp, roi, hbm_peak)
-        # the recompute-every-step figure beside the incremental one (and vice versa)
+        # beside the headline: the reference-style variants of the same workload, each a sub-run
+        #   value_recompute     re-conditioning on the target set from scratch at every step (as the reference)
+        #   value_full_storage  the full N x N covariance maintained (the reference's layout)
         if args.both:
-            other = "recompute" if inc else "incremental"
             del model, alg, gp, roi
             torch.cuda.empty_cache()
-            sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(max(3, args.steps // 4)),
-                                  "--warmup", "2", "--conditioning", other, "--workload", args.workload,
-                                  "--storage", args.storage, "--no-both", "--no-cpu"], capture_output=True, text=True)
-            try:
-                o = json.loads(sub.stdout.strip().splitlines()[-1])
-                line["value_" + other] = {"value": o["value"], "ms_per_step": o["ms_per_step"],
-                                          "e2e": o["e2e"]["value"], "kernels": o.get("kernels", [])}
-            except Exception as exc:  # pragma: no cover
-                line["value_" + other] = {"error": str(exc), "stderr": sub.stderr[-300:]}
+            variants = []
+            if inc:
+                variants.append(("value_recompute", ["--conditioning", "recompute", "--storage", args.storage]))
+            else:
+                variants.append(("value_incremental", ["--conditioning", "incremental", "--storage", args.storage]))
+            if args.storage == "lower":
+                variants.append(("value_full_storage", ["--conditioning", args.conditioning, "--storage", "full"]))
+            for key, extra in variants:
+                steps = max(3, args.steps // 4) if "recompute" in extra else args.steps
+                sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(steps), "--warmup", "3",
+                                      "--workload", args.workload, "--no-both", "--no-cpu"] + extra,
+                                     capture_output=True, text=True)
+                try:
+                    o = json.loads(sub.stdout.strip().splitlines()[-1])
+                    line[key] = {"value": o["value"], "ms_per_step": o["ms_per_step"], "e2e": o["e2e"]["value"],
+                                 "roofline": {k: o["roofline"][k] for k in ("kernel", "achieved", "frac", "ms_per_launch",
+                                                                            "algorithmic_bytes_per_launch")},
+                                 "kernels": o.get("kernels", [])}
+                except Exception as exc:  # pragma: no cover
+                    line[key] = {"error": str(exc), "stderr": sub.stderr[-300:]}
         if not args.no_cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu_oracle_sample(w, args.cpu_sample_n, 3, 1).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
@@ -541,7 +559,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--conditioning", default="incremental", choices=["incremental", "recompute"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--storage", default=os.environ.get("TAL_STORAGE", "full"), choices=["full", "lower"],
+    ap.add_argument("--storage", default=os.environ.get("TAL_STORAGE", "lower"), choices=["full", "lower"],
                     help="covariance storage: full N x N (reference layout) or lower-block (symmetric)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

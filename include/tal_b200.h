@@ -315,6 +315,21 @@ long long tal_cond_coef_bytes(long long m_pad);
  * tal_cond_chunk_scratch_bytes(ncols) bytes (may be null with chunks <= 1).  */
 long long tal_cond_chunk_scratch_bytes(long long ncols);
 
+/* Append form of the same incremental conditioning (csrc/condapp.cu): conditioning on
+ * the target set and on the observations commutes, so the conditioned GP is carried along
+ * by a growing factor  Wb = [W_0 (m_pad rows = L^-1 Sigma_A. at set-up); g_0; h_0; g_1; h_1; ...]
+ * ([cap_rows][ldw] fp64, `rows` rows in use): per observation ONE read-only pass
+ * kA = k + sum_j sign_j col_j Wb[j][:] (col = Wb[:, x*], signs -,...,-,(-,+)*), two appended
+ * rows g = kA / sqrt(kA[x*] + rho^2), h = k / sqrt(k[x*] + rho^2), and
+ * cs += g^2 - k w.  Traffic (m_pad + 2 t) ncols 8 bytes, nothing rewritten, no recurrence.
+ * scratch: tal_cond_append_scratch_bytes(ncols, n_split); the caller adds 2 to `rows`.  */
+int tal_cond_append_update(double* Wb, long long ldw, long long cap_rows, long long m_pad, long long rows,
+                           long long ncols, long long n_valid, long long cand0, const double* col,
+                           const void* kbuf_i, const void* wbuf_i, const double* rho_i,
+                           const long long* idx_dev, long long idx_host, double* cs, double* scratch,
+                           int n_split, int dtype, void* stream);
+long long tal_cond_append_scratch_bytes(long long ncols, int n_split);
+
 /* ---- masked arg-max -----------------------------------------------------
  * Replaces DiscreteGreedyAlgorithm._step's sample-region masking
  * (lib/algorithms/__init__.py:80) + MarginalModel.objective_argmax

@@ -357,11 +357,13 @@ def test_itl_directed_matches_oracle(cuda, N, m):
     assert np.argmax(F) == np.argmax(ref) or abs(ref[np.argmax(F)] - ref.max()) <= 1e-9 * max(1, abs(ref.max()))
 
 
+@pytest.mark.parametrize("form,capacity", [("append", 512), ("append", 7), ("downdate", 0)])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_incremental_conditioning_matches_recompute(cuda, dtype):
-    """The rank-1 downdate of L^-1 cov[A, :] (csrc/condinc.cu) against
-    re-conditioning from scratch at every step, over 60 observations, with the
-    reference's jitter^2 = 1e-10 (ill-conditioned Sigma_AA)."""
+def test_incremental_conditioning_matches_recompute(cuda, dtype, form, capacity):
+    """Incremental target-set conditioning — the append form (csrc/condapp.cu; with a
+    capacity of 7 observations it also re-bases every 7 steps) and the rank-1 downdate of
+    L^-1 cov[A, :] (csrc/condinc.cu) — against re-conditioning from scratch at every step,
+    over 60 observations, with the reference's jitter^2 = 1e-10 (ill-conditioned Sigma_AA)."""
     N, m, q = 1100, 200, 2
     rng = np.random.default_rng(21)
     domain = rng.random((N, 4))
@@ -369,6 +371,7 @@ def test_incremental_conditioning_matches_recompute(cuda, dtype):
     rho = np.stack([np.full(N, 0.1), 0.05 + 0.1 * rng.random(N)])
     beta = [1.0, 1.0]
     gp = _engine(cuda, covs, rho, dtype=dtype); gp.init_bounds(beta)
+    gp.cond_form, gp.cond_capacity = form, capacity
     fresh = _engine(cuda, covs, rho, dtype=dtype); fresh.init_bounds(beta)
     roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
     key = object()

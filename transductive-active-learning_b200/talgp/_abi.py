@@ -79,6 +79,9 @@ SIGNATURES = {
     "tal_cond_extract_col": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p]),
     "tal_cond_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _ll, _p, _p, _i, _p,
                              _i, _p]),
+    "tal_cond_append_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _ll, _p, _p, _i,
+                                    _i, _p]),
+    "tal_cond_append_scratch_bytes": (_ll, [_ll, _i]),
     "tal_cond_coef_bytes": (_ll, [_ll]),
     "tal_cond_chunk_scratch_bytes": (_ll, [_ll]),
     "tal_argmax_scratch_bytes": (_ll, []),

@@ -20,6 +20,7 @@ to the matrix diagonal by the update kernels.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -120,10 +121,15 @@ class DeviceGP:
         self._result = torch.zeros((4,), dtype=torch.int64, device=dev)  # tal_argmax_result
         self._result_host = torch.zeros((4,), dtype=torch.int64).pin_memory()
         self._y_host = torch.zeros((q,), dtype=torch.float64).pin_memory()
-        self._y_dev = torch.zeros((q,), **f64)
+        self._y_dev = torch.zeros((64, q), **f64)  # ring of device slots for host-supplied observations
+        self._y_slot, self._y_event = 0, None
         self._ws = {}  # named scratch tensors, grown on demand
         self._cond = None  # incremental conditioning state (score_itl_directed)
         self.cond_chunks = 0  # tal_cond_update: 0 = choose, 1 = single pass, > 1 = row-parallel
+        # incremental conditioning: "append" (read-only pass + two appended rows per observation,
+        # csrc/condapp.cu) or "downdate" (rewrites V every step, csrc/condinc.cu)
+        self.cond_form = os.environ.get("TAL_COND_FORM", "append")
+        self.cond_capacity = int(os.environ.get("TAL_COND_CAPACITY", "512"))  # observations before a rebase
         self._peer = None  # NVLink peer-memory exchange state (talgp.dist.PeerViews)
         if self.comm is not None:
             self._recs = torch.zeros((self.comm.world, 4), dtype=torch.int64, device=dev)
@@ -157,8 +163,8 @@ class DeviceGP:
             comm.table_ptr, comm.world, comm.rank, self._bounds_c, _ptr(self.cov), self.cov_stride_q,
             self.ld, self.N, self.q, int(self.lower), _ptr(idx_dev), int(idx_host), pv.kbuf_off,
             _ptr(st["V"]) if st is not None else None,
-            st["m_pad"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
-            st["m_pad"] if st is not None else 0, pv.pcol_off, self.cand0, self.n_cand, self.dt, _stream()),
+            st["cap"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
+            st["rows"] if st is not None else 0, pv.pcol_off, self.cand0, self.n_cand, self.dt, _stream()),
             "tal_peer_push_row")
         _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, comm.world, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
                                               self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
@@ -322,9 +328,15 @@ class DeviceGP:
         if isinstance(y, torch.Tensor) and y.is_cuda:
             y_dev = y
         else:
+            if self._y_event is not None:
+                self._y_event.synchronize()  # the previous async copy out of the pinned buffer is done
             self._y_host.copy_(torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1)))
-            self._y_dev.copy_(self._y_host, non_blocking=True)
-            y_dev = self._y_dev
+            self._y_slot = (self._y_slot + 1) % self._y_dev.shape[0]
+            y_dev = self._y_dev[self._y_slot]  # a fresh device slot: earlier steps may still read theirs
+            y_dev.copy_(self._y_host, non_blocking=True)
+            if self._y_event is None:
+                self._y_event = torch.cuda.Event()
+            self._y_event.record()
         if allreduce is not None:
             self.extract_row(idx_dev, idx_host)
             allreduce(self.kbuf)
@@ -544,26 +556,32 @@ class DeviceGP:
         reuse = incremental and st is not None and st["key"] is roi_key and st["valid"]
         if incremental and not reuse:
             m_pad, ncols = self._cond_dims(m)
-            if st is None or st["V"].shape != (self.q, m_pad, ncols):
+            append = self.cond_form == "append"
+            cap = m_pad + (2 * self.cond_capacity if append else 0)
+            if st is None or st["V"].shape != (self.q, cap, ncols):
                 self._cond = st = None  # drop the old buffers before allocating
-                st = dict(V=torch.empty((self.q, m_pad, ncols), dtype=torch.float64, device=self.device),
-                          cs=torch.empty((self.q, ncols), dtype=torch.float64, device=self.device),
-                          pcol=torch.empty((m_pad,), dtype=torch.float64, device=self.device),
-                          coef=torch.empty((int(self.lib.tal_cond_coef_bytes(m_pad)) // 8,),
-                                           dtype=torch.float64, device=self.device),
-                          chunk=torch.empty((int(self.lib.tal_cond_chunk_scratch_bytes(ncols)) // 8,),
-                                            dtype=torch.float64, device=self.device))
-            st.update(key=roi_key, m_pad=m_pad, ncols=ncols, valid=False)
+                f64 = dict(dtype=torch.float64, device=self.device)
+                st = dict(V=torch.zeros((self.q, cap, ncols), **f64), cs=torch.empty((self.q, ncols), **f64),
+                          pcol=torch.zeros((cap,), **f64))
+                if append:
+                    blocks = max(1, ncols // 512)
+                    st["n_split"] = int(max(1, min(64, m_pad // 64, -(-1184 // blocks))))
+                    st["app"] = torch.empty((int(self.lib.tal_cond_append_scratch_bytes(ncols, st["n_split"])) // 8,),
+                                            **f64)
+                else:
+                    st["coef"] = torch.empty((int(self.lib.tal_cond_coef_bytes(m_pad)) // 8,), **f64)
+                    st["chunk"] = torch.empty((int(self.lib.tal_cond_chunk_scratch_bytes(ncols)) // 8,), **f64)
+            st.update(key=roi_key, m_pad=m_pad, ncols=ncols, cap=cap, rows=m_pad, append=append, valid=False)
             self._cond = st
-            if self._peer is not None and self._peer.m_pad < m_pad:
-                self._peer_attach(m_pad)
+            if self._peer is not None and self._peer.m_pad < cap:
+                self._peer_attach(cap)
         if not incremental and st is not None:
             st["valid"] = False
         for i in range(self.q):
             if reuse:
                 cs = st["cs"][i, :n_out]
             elif incremental:
-                cs = self.cond_var_sumsq(i, roi_idx, m, jitter, V=st["V"][i], cs=st["cs"][i])
+                cs = self.cond_var_sumsq(i, roi_idx, m, jitter, V=st["V"][i, : st["m_pad"]], cs=st["cs"][i])
             else:
                 cs = self.cond_var_sumsq(i, roi_idx, m, jitter)
             _abi.check(self.lib.tal_score_itl_directed(
@@ -574,8 +592,14 @@ class DeviceGP:
         return F
 
     def _cond_downdate(self, idx_dev, idx_host, allreduce=None) -> None:
-        """After extract_row + step_vectors of an observation: V_i <- T^-1 (V_i - V_i[:, x] w^T)."""
+        """After exchange_row + step_vectors of an observation, carry the target-set
+        conditioning along: append form (csrc/condapp.cu) or V_i <- T^-1 (V_i - V_i[:, x] w^T)
+        (csrc/condinc.cu)."""
         st = self._cond
+        rows = st["rows"]
+        if st["append"] and rows + 2 > st["cap"]:
+            st["valid"] = False  # capacity reached: the next scoring pass re-conditions from scratch
+            return
         for i in range(self.q):
             V = st["V"][i]
             if self._peer is not None:  # the owner stored V[i][:, x] with the row (exchange_row)
@@ -583,14 +607,23 @@ class DeviceGP:
             else:
                 pcol = st["pcol"]
                 _abi.check(self.lib.tal_cond_extract_col(
-                    _ptr(V), st["ncols"], st["m_pad"], self.cand0, self.n_cand, _ptr(idx_dev),
+                    _ptr(V), st["ncols"], rows, self.cand0, self.n_cand, _ptr(idx_dev),
                     int(idx_host), _ptr(pcol), _stream()), "tal_cond_extract_col")
-                self._sum(pcol)
-            _abi.check(self.lib.tal_cond_update(
-                _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_cand, self.cand0,
-                _ptr(pcol), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
-                _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]),
-                int(self.cond_chunks), _ptr(st["chunk"]), self.dt, _stream()), "tal_cond_update")
+                self._sum(pcol[:rows])
+            if st["append"]:
+                _abi.check(self.lib.tal_cond_append_update(
+                    _ptr(V), st["ncols"], st["cap"], st["m_pad"], rows, st["ncols"], self.n_cand, self.cand0,
+                    _ptr(pcol), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]), _ptr(idx_dev),
+                    int(idx_host), _ptr(st["cs"][i]), _ptr(st["app"]), st["n_split"], self.dt, _stream()),
+                    "tal_cond_append_update")
+            else:
+                _abi.check(self.lib.tal_cond_update(
+                    _ptr(V), st["ncols"], st["m_pad"], st["ncols"], self.n_cand, self.cand0,
+                    _ptr(pcol), _ptr(self.kbuf[i]), _ptr(self.wbuf[i]), _ptr(self.rho[i]),
+                    _ptr(idx_dev), int(idx_host), _ptr(st["coef"]), _ptr(st["cs"][i]),
+                    int(self.cond_chunks), _ptr(st["chunk"]), self.dt, _stream()), "tal_cond_update")
+        if st["append"]:
+            st["rows"] = rows + 2
 
     def drop_conditioning(self) -> None:
         self._cond = None
