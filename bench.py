@@ -85,7 +85,7 @@ class ClockSampler:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=self.fh, stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -373,11 +373,11 @@ def run_ours(args, w):
             else:
                 gp.rank1_update()
 
+        clocks.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
         for _ in range(args.warmup):
             dev_step(False)
         torch.cuda.synchronize()
         lib.tal_reset_launch_count()
-        clocks.start()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):
@@ -496,12 +496,15 @@ def run_ours(args, w):
     # ---- N > 1: row-sharded -------------------------------------------------
     from talgp.dist import ShardedITLBench
     bench = ShardedITLBench(domain, A, table, w, world, rank, dev, args.conditioning, storage=args.storage)
-    for _ in range(args.warmup):
+    clocks.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
+    # a sharded step takes ~1 ms: warm up for a few hundred of them so that the clock sampler
+    # (one nvidia-smi sample per 50 ms) sees the loaded GPU before and during the timed region
+    warm_run = max(args.warmup, 200)
+    for _ in range(warm_run):
         bench.step(False)
     torch.cuda.synchronize()
     dist.barrier()
     lib.tal_reset_launch_count()
-    clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
@@ -532,7 +535,8 @@ def run_ours(args, w):
         achieved = alg_bytes / (rank1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": args.steps / (total_ms / 1e3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": warm_run,
+            "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload_config(args, w, world), exchange=exchange),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8,

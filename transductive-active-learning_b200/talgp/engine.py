@@ -129,7 +129,7 @@ class DeviceGP:
         # incremental conditioning: "append" (read-only pass + two appended rows per observation,
         # csrc/condapp.cu) or "downdate" (rewrites V every step, csrc/condinc.cu)
         self.cond_form = os.environ.get("TAL_COND_FORM", "append")
-        self.cond_capacity = int(os.environ.get("TAL_COND_CAPACITY", "512"))  # observations before a rebase
+        self.cond_capacity = int(os.environ.get("TAL_COND_CAPACITY", "1024"))  # observations before a rebase
         self._peer = None  # NVLink peer-memory exchange state (talgp.dist.PeerViews)
         if self.comm is not None:
             self._recs = torch.zeros((self.comm.world, 4), dtype=torch.int64, device=dev)
