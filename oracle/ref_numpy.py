@@ -24,6 +24,10 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = [
+    "ContinuousModel",
+    "LineBO",
+    "UnknownFunction",
+    "thompson_masks_from_samples",
     "DEFAULT_JITTER",
     "solve_linear_system",
     "noise_covariance_matrix",
@@ -739,3 +743,144 @@ class TableFunction:
     def observe(self, X):
         idx = get_indices(self.domain, np.asarray(X, dtype=np.float64))
         return self.y_table[:, idx]
+
+
+# --------------------------------------------------------------------------- #
+# continuous-domain model and LineBO (lib/model/continuous.py,
+# lib/algorithms/line_bo.py); 8f-4: Thompson-sampling masks (marginal.py:238-312)
+# --------------------------------------------------------------------------- #
+class UnknownFunction:
+    """lib/function/unknown.py:8-28."""
+
+    def __init__(self, q, f, use_objective_as_constraint: bool = False):
+        self.q = q
+        self.first_constraint = 0 if use_objective_as_constraint else 1
+        self._f = f
+
+    def observe(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        return np.array([np.asarray(self._f(X[j]), dtype=np.float64).reshape(-1) for j in range(X.shape[0])]).T
+
+
+class ContinuousModel:
+    """lib/model/continuous.py:15-95."""
+
+    def __init__(self, key, d, prior_kernels, beta, noise_rate, use_objective_as_constraint=False,
+                 X=None, y=None, prior_means=None):
+        q = len(prior_kernels)
+        self._key = key
+        self.q = q
+        self.first_constraint = 0 if use_objective_as_constraint else 1
+        self.beta = (lambda t: beta) if not callable(beta) else beta
+        self.noise_rate = noise_rate
+        self._prior_means = prior_means if prior_means is not None else [ZeroMean() for _ in range(q)]
+        self._prior_kernels = prior_kernels
+        self.X = X if X is not None else np.empty((0, d))
+        self.y = y if y is not None else np.empty((q, 0))
+
+    def acquire_key(self):
+        self._key = (int(self._key) * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        return self._key
+
+    def marginalize(self, X):  # :53-63
+        return MarginalModel(key=self.acquire_key(), domain=X, distrs=self.distrs(X), beta=self.beta,
+                             noise_rate=self.noise_rate,
+                             use_objective_as_constraint=self.first_constraint == 0, t=self.t)
+
+    @property
+    def t(self):
+        return self.X.shape[0]
+
+    def distr(self, X, i):  # :69-87
+        X = np.asarray(X, dtype=np.float64)
+        n, t = X.shape[0], self.t
+        X_train, y_train = self.X[:t], self.y[i, :t]
+        X_dom = np.concatenate((X, X_train), axis=0)
+        prior = GaussianDistribution.initialize(mean=self._prior_means[i], kernel=self._prior_kernels[i], X=X_dom)
+        posterior = prior.posterior(obs_idx=n + np.arange(t), obs=y_train,
+                                    obs_noise_std=self.noise_rate.at(X_train)[i])
+        return posterior.sub_distr(np.arange(n))
+
+    def distrs(self, X):
+        return [self.distr(X, i) for i in range(self.q)]
+
+    def step(self, X, y):  # :93-95
+        self.X = np.concatenate((self.X, np.asarray(X, dtype=np.float64)), axis=0)
+        self.y = np.concatenate((self.y, np.asarray(y, dtype=np.float64)), axis=1)
+
+
+class LineBO:
+    """lib/algorithms/line_bo.py:31-163 with the direction supplied by `_direction`."""
+
+    normalized_direction = None
+
+    def __init__(self, alg, model, bounds, n, eps, x_init=None):
+        self.alg, self.model, self.bounds, self.n, self.eps = alg, model, np.asarray(bounds, dtype=np.float64), n, eps
+        self._x_init = x_init if x_init is not None else self.origin
+        self.encountered_max = np.empty((0, self.bounds.shape[0]))
+
+    @property
+    def d(self):
+        return self.bounds.shape[0]
+
+    def _direction(self, f):
+        raise NotImplementedError
+
+    def _normalized_direction(self, f):  # :80-86 (the fallback draws a coordinate direction)
+        v = np.asarray(self._direction(f), dtype=np.float64)
+        norm = np.linalg.norm(v)
+        assert norm >= self.eps and not np.isinf(norm), "oracle: coordinate fallback needs a PRNG"
+        return v / norm
+
+    @property
+    def origin(self):
+        return (self.bounds[:, 0] + self.bounds[:, 1]) / 2
+
+    @property
+    def x_init(self):
+        return self._x_init if self.model.t == 0 else self.model.X[-1]
+
+    def subspace_bounds(self):  # :101-124
+        with np.errstate(divide="ignore", invalid="ignore"):
+            disp = ((self.bounds - self.x_init[:, None]) / self.normalized_direction[:, None]).reshape(-1)
+        pos, neg = disp[disp > 0], disp[disp <= 0]
+        if np.isinf(np.min(pos, initial=np.inf)):
+            pos, neg = disp[disp >= 0], disp[disp < 0]
+        return np.max(neg), np.min(pos)
+
+    def project(self, X):
+        return self.x_init + np.outer(X, self.normalized_direction)
+
+    def domain(self):  # :130-138
+        lo, hi = self.subspace_bounds()
+        return self.project(np.linspace(lo, hi, num=int((hi - lo) * self.n)))
+
+    def extended_domain(self):  # :140-146
+        return np.concatenate([self.model.X, self.domain(), self.encountered_max])
+
+    def step(self, f):  # :148-163
+        self.normalized_direction = self._normalized_direction(f)
+        domain = self.extended_domain()
+        model = self.model.marginalize(domain)
+        alg = self.alg(model)
+        X, y, result = alg._step(f, update_model=False)
+        self.model.step(X, y)
+        argmax = model.argmax
+        self.encountered_max = np.concatenate([self.encountered_max, argmax.reshape(1, -1)])
+        result["marginal_model"] = model
+        result["argmax"] = argmax
+        return result
+
+
+def thompson_masks_from_samples(samples, I, J):
+    """The per-sample logic of MarginalModel.thompson_sampling / _values (marginal.py:264-273,
+    304-310) on given samples [k, q, n]: (safety & optimality [k, n], safe optimum [k])."""
+    samples = np.asarray(samples, dtype=np.float64)
+    masks, values = [], []
+    for s in samples:
+        safety = np.all(s[J] >= 0, axis=0)
+        safe_optimum = np.max(np.min(np.where(safety, s[I], -np.inf), axis=0))
+        optimality = np.min(s[I], axis=0) >= np.repeat(safe_optimum, s.shape[1])
+        masks.append(safety & optimality)
+        values.append(safe_optimum)
+    return np.array(masks), np.array(values)

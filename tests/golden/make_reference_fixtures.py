@@ -18,6 +18,9 @@ writes
       GaussianDistribution.posterior (jitter and noise paths, repeated indices),
       MarginalModel.step with m = 0, 1, 5, sqd_correlation, the error messages of
       objective_argmax.
+  tests/golden/reference_next.npz           SURVEY 8f-2 / 8f-4: ContinuousModel.marginalize before
+      and after 7 observations, five LineBO steps along given directions (nested ITL-PM),
+      thompson_sampling / thompson_sampling_values on preset samples.
 
 This script needs /root/reference and is NOT run on the GPU box; the .npz files
 are committed.  The first thing it does is run the reference's own tests over the
@@ -232,6 +235,93 @@ def single_calls():
     return out
 
 
+def next_rows():
+    """ContinuousModel.marginalize, LineBO with a fixed sequence of
+    directions, the Thompson-sampling masks on preset samples."""
+    from lib.algorithms import ts_roi_constructor  # noqa: F401
+    from lib.algorithms.line_bo import LineBO, directed_alg_constructor
+    from lib.function.unknown import UnknownFunction
+    from lib.model.continuous import ContinuousModel
+    out = {}
+    rng = np.random.default_rng(7)
+    # ---- ContinuousModel (lib/model/continuous.py:15-95)
+    noise = HomoscedasticNoise(2, jnp.array([0.1, 0.2]))
+    ks = [stationary.Gaussian(lengthscale=0.8), stationary.Matern52(variance=1.5, lengthscale=0.6)]
+    cm = ContinuousModel(jr.PRNGKey(0), d=2, prior_kernels=ks, beta=jnp.array([2.0, 3.0]), noise_rate=noise)
+    Xq = rng.random((15, 2)) * 2 - 1
+    m0 = cm.marginalize(jnp.array(Xq))
+    out["cont/Xq"] = Xq
+    for tag, mm in (("t0", m0),):
+        out[f"cont/{tag}/means"], out[f"cont/{tag}/covariances"] = np.asarray(mm.means), np.asarray(mm.covariances)
+        out[f"cont/{tag}/l"], out[f"cont/{tag}/u"] = np.asarray(mm.l), np.asarray(mm.u)
+    Xa = rng.random((3, 2)) * 2 - 1
+    Xb = np.concatenate([rng.random((3, 2)) * 2 - 1, Xa[:1]])  # a repeated location
+    ya, yb = rng.standard_normal((2, 3)), rng.standard_normal((2, 4))
+    cm.step(jnp.array(Xa), jnp.array(ya))
+    cm.step(jnp.array(Xb), jnp.array(yb))
+    m7 = cm.marginalize(jnp.array(Xq))
+    out["cont/Xa"], out["cont/Xb"], out["cont/ya"], out["cont/yb"] = Xa, Xb, ya, yb
+    out["cont/t7/means"], out["cont/t7/covariances"] = np.asarray(m7.means), np.asarray(m7.covariances)
+    out["cont/t7/l"], out["cont/t7/u"], out["cont/t7/t"] = np.asarray(m7.l), np.asarray(m7.u), np.array(m7.t)
+    out["cont/t7/pess"] = np.asarray(m7.pessimistic_safe_set)
+    # ---- LineBO with given directions (lib/algorithms/line_bo.py:31-163)
+    dirs = np.array([[1.0, 0.0], [0.3, -0.8], [0.0, 1.0], [-0.6, 0.5], [1.0, 1.0]])
+
+    class FixedLineBO(LineBO):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self._it = 0
+
+        def _direction(self, f):
+            v = jnp.array(dirs[self._it])
+            self._it += 1
+            return v
+
+    bounds = np.array([[-1.0, 1.0], [-0.5, 1.5]])
+    fun = lambda x: jnp.array([jnp.exp(-jnp.sum((x - jnp.array([0.4, 0.6])) ** 2))])  # noqa: E731
+    f = UnknownFunction(q=1, f=fun, use_objective_as_constraint=True)
+    noise1 = HomoscedasticNoise(1, jnp.array([0.05]))
+    lm = ContinuousModel(jr.PRNGKey(1), d=2, prior_kernels=[stationary.Gaussian(lengthscale=0.5)],
+                         beta=jnp.array([2.0]), noise_rate=noise1, use_objective_as_constraint=True)
+    x0 = np.array([[0.1, 0.2]])
+    lm.step(jnp.array(x0), f.observe(jnp.array(x0)))  # a safe seed (f > 0 there)
+    lbo = FixedLineBO(alg=directed_alg_constructor(ITL, pm_roi_constructor), model=lm, bounds=jnp.array(bounds),
+                      n=12, eps=0.01)
+    out["linebo/dirs"], out["linebo/bounds"], out["linebo/x0"] = dirs, bounds, x0
+    for t in range(len(dirs)):
+        res = lbo.step(f)
+        mm = res["marginal_model"]
+        out[f"linebo/{t}/domain"] = np.asarray(mm.domain)
+        out[f"linebo/{t}/x"], out[f"linebo/{t}/y"] = np.asarray(res["x"]), np.asarray(res["y"])
+        out[f"linebo/{t}/F"], out[f"linebo/{t}/argmax"] = np.asarray(res["F"]), np.asarray(res["argmax"])
+        out[f"linebo/{t}/means"], out[f"linebo/{t}/variances"] = np.asarray(mm.means), np.asarray(mm.variances)
+        out[f"linebo/{t}/subspace_bounds"] = np.array([float(b) for b in lbo.subspace_bounds()])
+    out["linebo/final_X"], out["linebo/final_y"] = np.asarray(lm.X), np.asarray(lm.y)
+    out["linebo/encountered_max"] = np.asarray(lbo.encountered_max)
+    # ---- Thompson-sampling masks on preset samples (marginal.py:238-312)
+    N, q, k = 30, 3, 6
+    dom = rng.random((N, 2))
+    distrs = [GaussianDistribution(mean=jnp.zeros(N), covariance=jnp.eye(N)) for _ in range(q)]
+    tm = MarginalModel(jr.PRNGKey(2), jnp.array(dom), distrs, beta=jnp.array([1.0] * q),
+                       noise_rate=HomoscedasticNoise(q, jnp.array([0.1] * q)))
+    samples = rng.standard_normal((k, q, N))
+    samples[4, 1:] = -1.0  # a sample without any safe point
+    out["ts/samples"] = samples
+
+    def preset(which):
+        it = iter(range(k))
+        tm.sample = lambda k, keys=None: jnp.array(samples[next(it)][:, None, :])  # noqa: E731
+
+    for name, I, J in (("obj0_cons12", jnp.array([0]), jnp.arange(1, 3)),
+                       ("obj01_cons2", jnp.array([0, 1]), jnp.array([2])),
+                       ("obj0_nocons", jnp.array([0]), None)):
+        preset(name)
+        out[f"ts/{name}/mask"] = np.asarray(tm.thompson_sampling(k=k, I=I, J=J))
+        preset(name)
+        out[f"ts/{name}/values"] = np.asarray(tm.thompson_sampling_values(k=k, I=I, J=J))
+    return out
+
+
 def run_reference_tests():
     import pytest
     plug = os.path.join("/tmp", "refshim_plugin_dir")
@@ -247,13 +337,17 @@ def run_reference_tests():
 
 
 if __name__ == "__main__":
-    stages = sys.argv[1:] or ["tests", "calls", "traj"]
+    stages = sys.argv[1:] or ["tests", "calls", "next", "traj"]
     if "tests" in stages:
         run_reference_tests()
     if "calls" in stages:
         calls = single_calls()
         np.savez_compressed(os.path.join(HERE, "reference_calls.npz"), **calls)
         print("wrote", len(calls), "call arrays")
+    if "next" in stages:
+        nxt = next_rows()
+        np.savez_compressed(os.path.join(HERE, "reference_next.npz"), **nxt)
+        print("wrote", len(nxt), "next-row arrays")
     if "traj" in stages:  # minutes: the stand-in's vmap is a Python loop over all N^2 kernel pairs
         traj = {}
         runs = [(name, None) for name in problems.ALL] + [("c2", "CTL"), ("c4", "MMITL"), ("c1", "VTL"), ("c3", "VTL")]

@@ -128,6 +128,14 @@ def pm_roi_constructor(model: MarginalModel) -> ROI:
     return ROI.from_mask(model, model.potential_maximizers)
 
 
+def ts_roi_constructor(k: int) -> ROIConstructor:
+    """:127-132 — Thompson-sampling ROI with the constraint GPs as J."""
+    def ctor(model: MarginalModel) -> ROI:
+        J = torch.arange(model.first_constraint, model.q)
+        return ROI.from_mask(model, model.thompson_sampling(k=k, J=J))
+    return ctor
+
+
 def ucb_roi_constructor(model: MarginalModel) -> ROI:
     return ROI.from_mask(model, model.ucb)
 

@@ -67,6 +67,26 @@ class GaussianDistribution:
     def stddev(self) -> torch.Tensor:
         return torch.sqrt(self.variance)
 
+    def sub_distr(self, idx) -> "GaussianDistribution":
+        """:182-187 — the Gaussian limited to the points in `idx`."""
+        idx = torch.as_tensor(idx, device=self._gp.device).to(torch.int64).reshape(-1)
+        cov = self.covariance.index_select(0, idx).index_select(1, idx)
+        return GaussianDistribution(self.mean.index_select(0, idx), cov, dtype=self._gp.dtype,
+                                    storage=self._gp.storage)
+
+    def sample(self, key, sample_shape) -> torch.Tensor:
+        """:90-98 — independent functions from the Gaussian: mean + F z with
+        F F^T = covariance from ONE symmetric eigendecomposition (the reference's
+        method="svd" of a PSD matrix) and one GEMM for all samples.  The draws z come
+        from an integer key (lib/_random.py), not threefry."""
+        from lib import _random
+        shape = tuple(sample_shape) if not isinstance(sample_shape, int) else (sample_shape,)
+        n = self.n
+        w, v = torch.linalg.eigh(self.covariance.to(torch.float64))
+        factor = v * torch.sqrt(torch.clamp(w, min=0.0))[None, :]
+        z = _random.normal(key, shape + (n,))
+        return self.mean + z @ factor.T
+
     def _clone(self) -> "GaussianDistribution":
         src = self._gp
         src.ensure_full()

@@ -263,6 +263,61 @@ class MarginalModel(Model):
         vals = self.u[0, safe]
         return vals.max() if vals.numel() else torch.tensor(-np.inf, device=self.u.device)
 
+    @property
+    def pessimistic_max_u(self) -> torch.Tensor:
+        safe = self.pessimistic_safe_set
+        vals = self.u[0, safe]
+        return vals.max() if vals.numel() else torch.tensor(-np.inf, device=self.u.device)
+
+    # -- sampling (marginal.py:226-312) -----------------------------------------
+    def sample(self, k: int, keys=None) -> torch.Tensor:
+        """:226-236 — k independent functions from every GP: [q, k, n]."""
+        if keys is None:
+            keys = [self.acquire_key() for _ in range(self.q)]
+        return torch.stack([self.distr(i).sample(key=keys[i], sample_shape=(k,)) for i in range(self.q)])
+
+    def _ts_samples(self, k: int) -> torch.Tensor:
+        """[k, q, n]: one factorisation per GP and one GEMM for all k samples (the
+        reference factorises every GP again for every sample, :264-265)."""
+        return self.sample(k).permute(1, 0, 2)
+
+    @staticmethod
+    def thompson_masks_from_samples(samples: torch.Tensor, I, J):
+        """The per-sample logic of :264-273 on given samples [k, q, n]:
+        (safety & optimality [k, n], safe optimum [k])."""
+        I = torch.as_tensor(I, device=samples.device)
+        J = torch.as_tensor(J, device=samples.device)
+        n = samples.shape[2]
+        cons = samples[:, J] if J.dtype == torch.bool else samples.index_select(1, J.to(torch.int64))
+        obj = samples[:, I] if I.dtype == torch.bool else samples.index_select(1, I.to(torch.int64))
+        safety = (cons >= 0).all(dim=1) if cons.shape[1] > 0 else torch.ones(
+            (samples.shape[0], n), dtype=torch.bool, device=samples.device)
+        masked = torch.where(safety[:, None, :], obj, torch.full_like(obj, -np.inf))
+        safe_optimum = masked.min(dim=1).values.max(dim=1).values
+        optimality = obj.min(dim=1).values >= safe_optimum[:, None]
+        return safety & optimality, safe_optimum
+
+    def thompson_sampling(self, k: int, I=None, J=None, strict: bool = False) -> torch.Tensor:
+        """:238-278 — up to k points, each the safe maximum of an independent sample."""
+        if I is None:
+            I = torch.tensor([0])
+        assert torch.as_tensor(I).shape[0] > 0
+        if J is None:
+            J = torch.zeros(self.q, dtype=torch.bool)
+        masks, _ = self.thompson_masks_from_samples(self._ts_samples(k), I, J)
+        result = masks.any(dim=0)
+        if strict and int(result.sum()) == 0:
+            raise Exception("Thompson Sampling: No sample has a safe point.")
+        return result
+
+    def thompson_sampling_values(self, k: int, I=None, J=None) -> torch.Tensor:
+        """:280-312 — safe maxima of k independent samples."""
+        if I is None:
+            I = torch.tensor([0])
+        if J is None:
+            J = torch.zeros(self.q, dtype=torch.bool)
+        return self.thompson_masks_from_samples(self._ts_samples(k), I, J)[1]
+
     # -- arg-max ---------------------------------------------------------------
     def _argmax_index(self, F: torch.Tensor, sample_mask: Optional[torch.Tensor] = None):
         """Masked arg-max kernel + the reference's three error checks

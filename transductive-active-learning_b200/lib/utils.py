@@ -59,3 +59,13 @@ def is_subset_of(X, A) -> bool:
 def set_to_idx(arr) -> torch.Tensor:
     """lib/utils.py:74-75."""
     return torch.where(arr)[0]
+
+
+def grad_approx(x, f, h: float = 1e-3) -> torch.Tensor:
+    """lib/utils.py:27-41 — central finite differences of f at x."""
+    x = as_f64(x).reshape(-1)
+    d = x.shape[0]
+    eye = torch.eye(d, dtype=torch.float64, device=x.device)
+    X = torch.cat((x + h * eye, x - h * eye, x.reshape(1, -1)), dim=0)
+    sample = as_f64(f(X)).reshape(-1)
+    return (sample[:d] - sample[d: 2 * d]) / (2.0 * h)
