@@ -262,13 +262,13 @@ def workload_config(args, w, world):
     return {
         "workload": (f"BASELINE configs[{4 if args.workload == 'c5' else 2}]: synthetic transductive ITL, "
                      f"N={w['N']} candidates, target set m={w['m']}, d={w['d']} Matern-5/2 "
-                     f"(l={w['lengthscale']}), q=1, rho={w['rho']}, fp64"),
+                     f"(l={w['lengthscale']}), q=1, rho={w['rho']}, {'fp32' if getattr(args, 'dtype', 'f64') == 'f32' else 'fp64'}"),
         "name": args.workload, "N": w["N"], "m": w["m"], "d": w["d"], "q": 1,
         "conditioning": args.conditioning,
         "storage": ("full N x N covariance (reference layout)" if args.storage == "full" else
                     "lower-block: only the blocks on or below the diagonal are maintained (symmetric matrix)"),
         "l2": "inputs larger than L2 (covariance %.1f GB per GPU >> 126 MB): no flush needed"
-              % (w["N"] * w["N"] * 8 / world / 1e9),
+              % (w["N"] * w["N"] * (4 if getattr(args, "dtype", "f64") == "f32" else 8) / world / 1e9),
         "parallelism": "1 GPU" if world == 1 else f"covariance row-sharded over {world} GPUs",
     }
 
@@ -334,7 +334,8 @@ def run_ours(args, w):
             nz = HomoscedasticNoise(1, np.array([rho]))
             distrs = prior_distr(nz, domain, np.zeros((0, w["d"])), np.zeros((1, 0)),
                                  [stationary.Matern52(lengthscale=w["lengthscale"])], [ZeroMean()],
-                                 storage=args.storage)
+                                 storage=args.storage,
+                                 dtype=torch.float32 if args.dtype == "f32" else torch.float64)
             model = MarginalModel(0, domain, distrs, beta=np.array(beta), noise_rate=nz)
             alg = ITL(model, index_roi_constructor(A), conditioning=args.conditioning)
             alg.sample_mask()  # static; computed once (lib/algorithms/__init__.py:80)
@@ -425,7 +426,7 @@ def run_ours(args, w):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, w, 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
@@ -439,7 +440,8 @@ def run_ours(args, w):
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rank1_ms,
                          "share_of_step": rank1_ms / (total_ms / args.steps),
                          "frac_of_8TBs_datasheet": achieved / 8000.0,
-                         "effective_GBs_vs_full_matrix_bytes": 2.0 * model.q * N * N * 8 / (rank1_ms * 1e-3) / 1e9},
+                         "effective_GBs_vs_full_matrix_bytes": 2.0 * model.q * N * N * (4 if args.dtype == "f32" else 8)
+                                                               / (rank1_ms * 1e-3) / 1e9},
         }
         # the scoring pass of this mode next to the dominant kernel (north_star: HBM GB/s of the
         # rank-1 update AND the scoring pass; tensor-pipe utilisation of the TRSM in recompute mode)
@@ -474,6 +476,9 @@ def run_ours(args, w):
                 variants.append(("value_incremental", ["--conditioning", "incremental", "--storage", args.storage]))
             if args.storage == "lower":
                 variants.append(("value_full_storage", ["--conditioning", args.conditioning, "--storage", "full"]))
+            if args.dtype == "f64":
+                variants.append(("value_fp32_storage", ["--conditioning", args.conditioning, "--storage", args.storage,
+                                                        "--dtype", "f32"]))
             for key, extra in variants:
                 steps = max(3, args.steps // 4) if "recompute" in extra else args.steps
                 sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", str(steps), "--warmup", "3",
@@ -565,6 +570,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--storage", default=os.environ.get("TAL_STORAGE", "lower"), choices=["full", "lower"],
                     help="covariance storage: full N x N (reference layout) or lower-block (symmetric)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="covariance storage / arithmetic type (the reference's only mode is f64)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-both", dest="both", action="store_false",

@@ -181,7 +181,8 @@ int tal_gather_rows(const void* cov, long long ld, long long row0, long long n_l
 int tal_small_posterior_weights(const double* B, long long ldb, long long N,
                                 const long long* obs_idx, int m, const double* noise_std,
                                 double jitter, const double* y, double* W, double* mean,
-                                double* var, void* stream);
+                                double* var, double* scratch, void* stream);
+long long tal_small_scratch_bytes(void); /* size of `scratch` (device) */
 int tal_rankm_update(void* cov, long long ld, long long row0, long long n_loc, long long N,
                      const double* B, const double* W, long long ldb, int m, int dtype,
                      void* stream);

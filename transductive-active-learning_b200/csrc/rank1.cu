@@ -655,18 +655,10 @@ int tal_gather_rows(const void* cov, long long ld, long long row0, long long n_l
 int tal_small_posterior_weights(const double* B, long long ldb, long long N,
                                 const long long* obs_idx, int m, const double* noise_std,
                                 double jitter, const double* y, double* W, double* mean,
-                                double* var, void* stream) {
-  TAL_ARG(B && obs_idx && y && W && mean && var);
+                                double* var, double* scratch, void* stream) {
+  TAL_ARG(B && obs_idx && y && W && mean && var && scratch);
   TAL_ARG(m >= 1 && m <= kSmallM);
-  // scratch for L and delta lives at the tail of W's allocation: the caller
-  // provides W with (m + m + 1) rows? No: keep it simple and use a static
-  // per-process scratch (one stream at a time per device, as the ABI states).
-  static double* scratch[64] = {nullptr};
-  int dev = 0;
-  TAL_CUDA(cudaGetDevice(&dev));
-  TAL_ARG(dev < 64);
-  if (!scratch[dev]) TAL_CUDA(cudaMalloc(&scratch[dev], sizeof(double) * (kSmallM * kSmallM + kSmallM)));
-  double* Lg = scratch[dev];
+  double* Lg = scratch;  // tal_small_scratch_bytes(): the m x m factor and the m residuals
   double* delta = Lg + kSmallM * kSmallM;
   cudaStream_t st = as_stream(stream);
   small_chol_kernel<<<1, 256, 0, st>>>(B, ldb, obs_idx, m, noise_std, jitter, Lg);
@@ -678,6 +670,8 @@ int tal_small_posterior_weights(const double* B, long long ldb, long long N,
   TAL_LAUNCH_CHECK("tal_small_posterior_weights/solve");
   return TAL_OK;
 }
+
+long long tal_small_scratch_bytes(void) { return (long long)sizeof(double) * (kSmallM * kSmallM + kSmallM); }
 
 int tal_rankm_update(void* cov, long long ld, long long row0, long long n_loc, long long N,
                      const double* B, const double* W, long long ldb, int m, int dtype,

@@ -56,7 +56,8 @@ SIGNATURES = {
                               _p, _p, _p, _p, _i, _p]),
     "tal_rank1_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _i, _i, _p]),
     "tal_gather_rows": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _ll, _i, _p]),
-    "tal_small_posterior_weights": (_i, [_p, _ll, _ll, _p, _i, _p, _d, _p, _p, _p, _p, _p]),
+    "tal_small_posterior_weights": (_i, [_p, _ll, _ll, _p, _i, _p, _d, _p, _p, _p, _p, _p, _p]),
+    "tal_small_scratch_bytes": (_ll, []),
     "tal_rankm_update": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p]),
     "tal_bounds_masks": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p]),
     "tal_mask_to_indices": (_i, [_p, _ll, _p, _p, _p]),

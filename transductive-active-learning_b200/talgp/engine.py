@@ -363,6 +363,7 @@ class DeviceGP:
         if noise_std is not None:
             noise_std = noise_std.to(device=self.device, dtype=torch.float64).contiguous()
         ldb = self.ld
+        small = self._scratch("cond_small", (int(self.lib.tal_small_scratch_bytes()) // 8,))
         for s in range(0, m_total, 64):
             e = min(m_total, s + 64)
             m = e - s
@@ -380,7 +381,7 @@ class DeviceGP:
             _abi.check(self.lib.tal_small_posterior_weights(
                 _ptr(B), ldb, self.N, _ptr(oi), m,
                 _ptr(noise_std[s:e]) if noise_std is not None else None, float(jitter),
-                _ptr(y[s:e]), _ptr(W), _ptr(self.mean[i]), _ptr(self.var[i]), _stream()),
+                _ptr(y[s:e]), _ptr(W), _ptr(self.mean[i]), _ptr(self.var[i]), _ptr(small), _stream()),
                 "tal_small_posterior_weights")
             update = self.lib.tal_rankm_update_lower if self.lower else self.lib.tal_rankm_update
             _abi.check(update(
