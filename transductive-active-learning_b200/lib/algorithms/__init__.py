@@ -64,7 +64,9 @@ class DiscreteGreedyAlgorithm(GreedyAlgorithm):
         y = f.observe(X)
         if update_model:
             self.model.step(X=X, y=y)
-        y = y if isinstance(y, torch.Tensor) else as_f64(y)
+        if not isinstance(y, torch.Tensor):  # a host black box: keep its observation on the host
+            import numpy as np
+            y = torch.as_tensor(np.asarray(y, dtype=np.float64))
         return X, y, {"x": X[0], "y": y[:, 0], "F": F, "F_max": F[idx]}
 
     def step(self, f: Function) -> dict:

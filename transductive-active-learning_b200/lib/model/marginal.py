@@ -218,6 +218,12 @@ class MarginalModel(Model):
         """:193-195 with is_subset_of's scalar-wise `isin` semantics (utils.py:65-71)."""
         if not isinstance(A, ROI):
             return is_subset_of(self.domain[self.operating_safe_set], A)
+        # no constraint GP and the default operating safe set: the safe set is the whole domain at
+        # every step (an `all` over an empty set, :176-184), so the answer for a fixed ROI never changes
+        static = (self.first_constraint >= self.q and A.fixed
+                  and type(self).operating_safe_set is MarginalModel.operating_safe_set)
+        if static and getattr(A, "_covers_domain", None) is not None:
+            return A._covers_domain
         import ctypes as C
         sid, n_sid = self._sid_table()
         gp = self._gp
@@ -229,7 +235,10 @@ class MarginalModel(Model):
             C.c_void_p(A.idx.data_ptr()), None, A.m, C.c_void_p(present.data_ptr()),
             C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
             "tal_scalar_subset")
-        return bool(out.item())
+        res = bool(out.item())
+        if static:
+            A._covers_domain = res
+        return res
 
     @property
     def potential_expanders(self) -> torch.Tensor:
@@ -348,9 +357,11 @@ class MarginalModel(Model):
         beta = self._beta_now()  # evaluated at the OLD t (:366-368)
         if m == 1:
             X_idx = self.get_indices(X)  # device int64[1]
-            yv = y if (isinstance(y, torch.Tensor) and y.is_cuda) else as_f64(y)
-            self._gp.observe(X_idx, yv.reshape(-1)[: self.q] if yv.numel() == self.q
-                             else yv[:, 0].contiguous(), beta)
+            if isinstance(y, torch.Tensor) and y.is_cuda:
+                yv = y.reshape(-1)[: self.q] if y.numel() == self.q else y[:, 0].contiguous()
+            else:  # host observation: staged through the engine's pinned buffer, asynchronous H2D
+                yv = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y, dtype=np.float64).reshape(self.q, -1)[:, 0]
+            self._gp.observe(X_idx, yv, beta)
         elif m > 1:
             X_idx = self.get_indices(X)
             noise_rate = self.noise_rate.at(X)
