@@ -136,7 +136,7 @@ int tal_rank1_update(void* cov, long long cov_stride_q, long long ld, long long 
  * The posterior covariance is symmetric (up to the rounding of k_a w_b versus
  * k_b w_a), so an opt-in storage mode maintains only the blocks on or below the
  * diagonal: of global row g the columns [0, cend(g)), cend(g) = min(ld,
- * (g / B + 1) * B), B = tal_sym_block(dtype) elements (8 KiB of a row).  Entry
+ * (g / B + 1) * B), B = tal_sym_block(dtype) = 32 elements (the rows of one update CTA).  Entry
  * (g, c) with c >= cend(g) is read as (c, g).  The allocation and addressing are
  * unchanged ([q][n_loc][ld]); the blocks above the diagonal are simply not
  * touched, which halves the HBM traffic of the rank-1 update.

@@ -340,7 +340,7 @@ int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* 
   TAL_ARG(bounds.b[0] == 0 && bounds.b[G] == N);
   for (int g = 0; g < G; ++g) TAL_ARG(bounds.b[g] <= bounds.b[g + 1] && bounds.b[g] % 4 == 0);
   const i64 vn = dtype == TAL_F64 ? 2 : 4;
-  const i64 blk = lower ? (dtype == TAL_F64 ? 1024 : 2048) : 0;
+  const i64 blk = lower ? tal_sym_block(dtype) : 0;
   i64 span = (ld + vn - 1) / vn;
   if (V && m_pad > span) span = m_pad;
   dim3 grid((unsigned)((span + 255) / 256), q, G);

@@ -12,7 +12,8 @@ namespace tal {
 
 // Lower-block ("symmetric") storage: of global row g only the columns
 // [0, sym_cend(g)) are maintained; entry (g, c) with c >= sym_cend(g) is read as
-// (c, g).  sym_block is a multiple of the CTA tiles (rows and columns).
+// (c, g).  sym_block (32 elements) is the row count of an update CTA and a multiple
+// of the per-thread vector width.
 __device__ __forceinline__ i64 sym_cend(i64 grow, i64 block, i64 ld) {
   const i64 e = (grow / block + 1) * block;
   return e < ld ? e : ld;
@@ -190,8 +191,9 @@ rank1_ldg32_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_lo
   const i64 col = (ct * 256 + threadIdx.x) * VN;
   if (col >= ld) return;
   const i64 r0 = rb * rows_per_cta;
-  // only the blocks on or below the diagonal are kept (the CTA's rows share one sym block)
-  if (sym_block > 0 && ct * 256 * VN >= sym_cend(row0 + r0, sym_block, ld)) return;
+  // only the blocks on or below the diagonal are kept (the CTA's 32 rows share one sym block):
+  // whole tiles above it exit here, the tile that straddles it is cut per thread
+  if (sym_block > 0 && col >= sym_cend(row0 + r0, sym_block, ld)) return;
   T* C = cov + gp * stride_q + col;
   const T* k = kbuf + (i64)gp * ld + row0;
   V wv = *reinterpret_cast<const V*>(wbuf + (i64)gp * ld + col);
@@ -508,7 +510,7 @@ rankm_update_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N,
   const i64 col = (i64)blockIdx.y * 256 + threadIdx.x;
   if (col >= N) return;
   const i64 r0 = (i64)blockIdx.x * rows_per_cta;
-  if (sym_block > 0 && (i64)blockIdx.y * 256 >= sym_cend(row0 + r0, sym_block, ld)) return;
+  if (sym_block > 0 && col >= sym_cend(row0 + r0, sym_block, ld)) return;
   double w[kSmallM];
   for (int j = 0; j < m; ++j) w[j] = W[(i64)j * ldb + col];
   const i64 r1 = min(n_loc, r0 + (i64)rows_per_cta);
@@ -590,7 +592,7 @@ static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
     const unsigned row_blocks = (unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta);
     const unsigned col_tiles = (unsigned)((ld + 256 * VN - 1) / (256 * VN));
     if (sym_block > 0) {
-      TAL_ARG(sym_block % (256 * VN) == 0 && sym_block % rows_per_cta == 0 && row0 % rows_per_cta == 0);
+      TAL_ARG(sym_block % VN == 0 && sym_block % rows_per_cta == 0 && row0 % rows_per_cta == 0);
       TAL_ARG(row_blocks <= 65535);
     }
     dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
@@ -691,7 +693,7 @@ int tal_rankm_update(void* cov, long long ld, long long row0, long long n_loc, l
 }
 
 /* ---- lower-block ("symmetric") storage ------------------------------------ */
-long long tal_sym_block(int dtype) { return dtype == TAL_F64 ? 1024 : 2048; }
+long long tal_sym_block(int dtype) { (void)dtype; return 32; }
 
 int tal_rank1_update_lower(void* cov, long long cov_stride_q, long long ld, long long row0,
                            long long n_loc, long long N, int q, const void* kbuf, const void* wbuf,

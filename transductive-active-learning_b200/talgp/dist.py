@@ -34,9 +34,8 @@ def shard_bounds(N: int, world: int, align: int = 64, storage: str = "full") -> 
     lower-block storage: the kept part of row r is ~r columns long, so the
     boundaries sit at N sqrt(g / world) to balance the update traffic."""
     if storage == "lower":
-        # exact cost model: row r keeps cend(r) = min(ld, (r // B + 1) * B) columns (B = 1024 fp64
-        # elements; the fp32 block is twice as long, the split below stays within 1 % of even)
-        B, ld = 1024, -(-N // 32) * 32
+        # exact cost model: row r keeps cend(r) = min(ld, (r // B + 1) * B) columns, B = tal_sym_block = 32
+        B, ld = 32, -(-N // 32) * 32
         cend = np.minimum((np.arange(N, dtype=np.int64) // B + 1) * B, ld)
         cum = np.concatenate([[0], np.cumsum(cend)])
         b = [0]
