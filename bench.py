@@ -378,6 +378,7 @@ def run_ours(args, w):
         for _ in range(args.warmup):
             dev_step(False)
         torch.cuda.synchronize()
+        l_start, u_start = gp.l.clone(), gp.u.clone()
         lib.tal_reset_launch_count()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -390,6 +391,14 @@ def run_ours(args, w):
         rank1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         status = gp.read_result().status
         assert status == 0, f"arg-max status {status}"
+        # size-independent invariants of the state after the timed steps (full size, no oracle needed)
+        invariants = {
+            "var_equals_diag_cov_bitwise": bool(torch.equal(torch.diagonal(gp.cov[0, :, :N]).to(torch.float64), gp.var[0])),
+            "state_finite": bool(torch.isfinite(gp.mean).all() and torch.isfinite(gp.var).all()),
+            "variances_positive": bool((gp.var > 0).all()),
+            "bounds_are_running_intersections": bool((gp.l >= l_start).all() and (gp.u <= u_start).all()),
+        }
+        assert all(invariants.values()), invariants
 
         # ---- end to end through the drop-in API with a host black box ---------
         class HostFunction(Function):
@@ -430,7 +439,7 @@ def run_ours(args, w):
             "config": workload_config(args, w, 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "invariants": invariants,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": {"kernel": "rank1_update (tal_rank1_update%s)" % ("_lower" if args.storage == "lower" else ""),
                          "bound": "hbm", "achieved": achieved,
@@ -525,6 +534,25 @@ def run_ours(args, w):
     launches = int(lib.tal_launch_count())
     e2e_ms = bench.e2e(args.steps)
     clk = clocks.stop()
+    # size-independent invariants at full size: every rank selected the same candidates, the replicated
+    # vectors are identical on all ranks, var == diag(cov) bit for bit on the rows this rank holds
+    g = bench.gp
+    sel = g._combined[0:1].clone()
+    sel_all = [torch.zeros_like(sel) for _ in range(world)]
+    dist.all_gather(sel_all, sel)
+    digest = torch.stack([g.mean.sum(), g.var.sum(), g.l.sum(), g.u.sum()])
+    dig_all = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(dig_all, digest)
+    rows = torch.arange(g.row0, g.row0 + g.n_loc, device=dev)
+    diag_ok = torch.equal(g.cov[0, torch.arange(g.n_loc, device=dev), rows], g.var[0, rows])
+    ok = torch.tensor([int(diag_ok and bool(torch.isfinite(g.var).all()) and bool((g.var > 0).all()))], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    invariants = {
+        "ranks_agree_on_selection": all(bool(torch.equal(s, sel_all[0])) for s in sel_all),
+        "replicated_state_identical": all(bool(torch.equal(d, dig_all[0])) for d in dig_all),
+        "var_equals_diag_cov_bitwise_and_positive_all_ranks": bool(int(ok) == 1),
+    }
+    assert all(invariants.values()), invariants
     exchange = "nccl"
     if getattr(bench.gp.comm, "peer", False):
         exchange = "nvlink-peer-memory"
@@ -546,9 +574,10 @@ def run_ours(args, w):
             "data": "synthetic", "config": dict(workload_config(args, w, world), exchange=exchange),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8,
                     "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "invariants": invariants,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-            "roofline": {"kernel": "rank1_update (tal_rank1_update), per GPU, max over ranks", "bound": "hbm",
+            "roofline": {"kernel": "rank1_update (tal_rank1_update%s), per GPU, max over ranks" % (
+                "_lower" if args.storage == "lower" else ""), "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": peak_src, "traffic": ncu_traffic("rank1_", args.workload, world, args.storage),
                          "algorithmic_bytes_per_launch": alg_bytes,
