@@ -241,6 +241,14 @@ int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
                     const long long* roi_idx, long long m, const double* row_weight,
                     const double* dinv, double p0, double p1, double* c_out, int dtype,
                     void* stream);
+/* lower-block storage (tal_rank1_update_lower): the same column sums over ALL candidates x from what
+ * this shard keeps — the kept part of its ROI rows plus, for its own rows x, the ROI entries mirrored
+ * into row x.  Every pair (a, x) is counted exactly once across the shards; a sum over the shards
+ * completes c_out [N] (one GPU: it is complete).  dinv is the full [N] vector. */
+int tal_colsum_lower(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                     long long N, const long long* roi_idx, long long m, const double* row_weight,
+                     const double* dinv, double p0, double p1, double* part, int n_split,
+                     double* c_out, int dtype, void* stream);
 int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,
                   void* stream);
 int tal_roi_weights(const double* var, const long long* roi_idx, long long m, int reciprocal,

@@ -89,7 +89,8 @@ def test_general_m_conditioning_lower(cuda):
     torch.testing.assert_close(low.covariances_view(), full.covariances_view(), rtol=1e-10, atol=1e-13)
 
 
-@pytest.mark.parametrize("name,rule", [("c1", None), ("c2", None), ("c3", None), ("c4", None), ("c2", "CTL")])
+@pytest.mark.parametrize("name,rule", [("c1", None), ("c2", None), ("c3", None), ("c4", None), ("c2", "CTL"),
+                                       ("c4", "MMITL"), ("c3", "VTL")])
 def test_lower_storage_matches_reference_trajectories(cuda, name, rule):
     """The drop-in API over a lower-block model against the golden vectors made by
     the reference's own source (tests/golden/reference_trajectories.npz)."""
@@ -116,6 +117,7 @@ def test_lower_storage_matches_reference_trajectories(cuda, name, rule):
     for attr in ("means", "variances", "l", "u"):
         np.testing.assert_allclose(getattr(model, attr).cpu().numpy(), TRAJ[f"{tag}/{attr}"], err_msg=attr,
                                    rtol=1e-10, atol=1e-11)
+    assert model._gp._upper_stale  # no scoring rule needed the mirrored blocks
     cov = model.covariances
     torch.testing.assert_close(torch.diagonal(cov, dim1=1, dim2=2), model.variances, rtol=0, atol=0)
 

@@ -135,12 +135,11 @@ def test_sharded_vtl_columns_match_rows(cuda):
 
 
 @pytest.mark.parametrize("name,storage", [("c1", "full"), ("c2", "full"), ("c3", "full"), ("c4", "full"),
-                                          ("c1", "lower"), ("c3", "lower")])
+                                          ("c1", "lower"), ("c2", "lower"), ("c3", "lower"), ("c4", "lower")])
 def test_drop_in_api_row_sharded(cuda, name, storage):
     """The `lib.*` classes over a row-sharded model (3 ranks emulated by threads):
-    same selections, scores and posterior as the single-GPU model.  (Lower-block
-    storage: the ITL rules; the VTL-type rules read full rows and need full storage
-    on a sharded model.)"""
+    same selections, scores and posterior as the single-GPU model, in both storage
+    modes (lower-block storage: the VTL-type rules sum what every shard keeps)."""
     import problems
     from talgp.dist import ThreadComm
     p = problems.ALL[name]()

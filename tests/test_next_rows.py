@@ -192,3 +192,53 @@ def test_sampling_statistics_and_ts_roi(cuda):
     alg = ITL(model, ts_roi_constructor(8))
     res = alg.step(TableFunction(model.domain, table))
     assert res["F"].shape == (N,) and model.t == 1
+
+
+# ---- the reference's own tests, restated over the drop-in classes ---------------------------------
+@pytest.mark.gpu
+def test_reference_test_continuous_model(cuda):
+    """tests/test_continuous_model.py of the reference: prior state of a marginalised model is exact,
+    sample() has the documented shape, step() changes the marginal means."""
+    import torch
+    from lib.gp import kernels
+    from lib.model.continuous import ContinuousModel
+    from lib.noise import HomoscedasticNoise
+    noise_rate = HomoscedasticNoise(q=1, noise_rates=np.array([0.1]))
+    model = ContinuousModel(key=0, d=1, prior_kernels=[kernels.stationary.Gaussian(lengthscale=1)],
+                            beta=np.array([1.0]), noise_rate=noise_rate, use_objective_as_constraint=True)
+    X = torch.tensor([[-1.0], [-0.5], [0.0], [0.5], [1.0]], dtype=torch.float64, device=cuda)
+    N = X.shape[0]
+    mm = model.marginalize(X)
+    assert bool((mm.means == torch.zeros((1, N), device=cuda, dtype=torch.float64)).all())      # :30-31
+    assert bool((mm.stddevs == torch.ones((1, N), device=cuda, dtype=torch.float64)).all())     # :34-35
+    assert bool((mm.l == -1.0).all()) and bool((mm.u == 1.0).all())                             # :38-40
+    assert mm.sample(k=10).shape == (1, 10, N)                                                  # :43-44
+    model.step(X, torch.sin(X).T)                                                               # :47-51
+    assert bool((model.marginalize(X).means != 0).any())
+
+
+@pytest.mark.gpu
+def test_reference_test_line_bo(cuda):
+    """tests/test_line_bo.py of the reference: Random / Coordinate / Descent LineBO return unit-length
+    directions."""
+    import torch
+    from lib.algorithms import DiscreteGreedyAlgorithm
+    from lib.algorithms.line_bo import CoordinateLineBO, DescentLineBO, RandomLineBO, alg_constructor
+    from lib.function.unknown import UnknownFunction
+    from lib.gp import kernels
+    from lib.model.continuous import ContinuousModel
+    from lib.noise import HomoscedasticNoise
+
+    class DummyAlg(DiscreteGreedyAlgorithm):
+        def F(self):
+            pass
+
+    D = 2
+    model = ContinuousModel(key=0, d=D, prior_kernels=[kernels.stationary.Gaussian()], beta=np.array([1.0]),
+                            noise_rate=HomoscedasticNoise(q=1, noise_rates=np.array([0.1])),
+                            use_objective_as_constraint=True)
+    bounds = np.array([[-1.0, 1.0], [0.0, 1.0]])
+    f = UnknownFunction(q=1, f=lambda x: torch.linalg.norm(x).reshape(1))
+    kw = dict(alg=alg_constructor(DummyAlg), model=model, bounds=bounds, n=10, eps=0.01)
+    for lbo in (RandomLineBO(**kw), CoordinateLineBO(**kw), DescentLineBO(m=2 * D, alpha=0.1, **kw)):
+        assert float(torch.linalg.norm(lbo._normalized_direction(f))) == pytest.approx(1, abs=1e-5)

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256)
 colsum_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N,
                    const i64* __restrict__ roi_idx, i64 m, const double* __restrict__ row_weight,
                    const double* __restrict__ dinv, double p0, double p1,
-                   double* __restrict__ part) {
+                   double* __restrict__ part, i64 sym_block) {
   typedef typename Vec16<T>::type V;
   constexpr int VN = Vec16<T>::n;
   const i64 col = ((i64)blockIdx.x * 256 + threadIdx.x) * VN;
@@ -69,8 +69,11 @@ colsum_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N
     for (int t = 0; t < UNROLL; ++t) {
       ok[t] = false;
       if (j + t < j1) {
-        const i64 r = roi_idx[j + t] - row0;
-        if (r >= 0 && r < n_loc) {
+        const i64 a = roi_idx[j + t];
+        const i64 r = a - row0;
+        // lower-block storage: only the kept part of row a (columns below its diagonal block's
+        // end); the pairs (a, x) beyond it are read from row x by colsum_cols_kernel
+        if (r >= 0 && r < n_loc && (sym_block == 0 || col < (a / sym_block + 1) * sym_block)) {
           ok[t] = true;
           c[t] = ld_stream(reinterpret_cast<const V*>(cov + r * ld + col));
           wa[t] = row_weight ? row_weight[j + t] : 1.0;
@@ -113,19 +116,26 @@ template <typename T, int RULE>
 __global__ void __launch_bounds__(256)
 colsum_cols_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, const i64* __restrict__ roi_idx,
                    i64 m, const double* __restrict__ row_weight, const double* __restrict__ dinv,
-                   double p0, double p1, double* __restrict__ out) {
+                   double p0, double p1, double* __restrict__ out, i64 sym_block, i64 row0,
+                   int accumulate) {
   const i64 r = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n_loc) return;
   const T* row = cov + r * ld;
   const double di = dinv ? dinv[r] : 0.0;
+  // lower-block storage: row x = row0 + r holds the pairs (a, x) of the ROI points a whose own
+  // kept part ends at or before x, i.e. a below the start of x's diagonal block
+  const i64 a_end = sym_block > 0 ? ((row0 + r) / sym_block) * sym_block : (i64)0x7fffffffffffffffLL;
   double acc = 0.0;
   for (i64 j = lane; j < m; j += 32) {
-    const double v = (double)row[roi_idx[j]];
-    acc += elem<RULE>(v, row_weight ? row_weight[j] : 1.0, di, p0, p1);
+    const i64 a = roi_idx[j];
+    if (a < a_end) {
+      const double v = (double)row[a];
+      acc += elem<RULE>(v, row_weight ? row_weight[j] : 1.0, di, p0, p1);
+    }
   }
   acc = warp_sum(acc);
-  if (lane == 0) out[r] = acc;
+  if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
 }
 
 // tr_A = sum_{a in roi} var[a]  (one block, deterministic)
@@ -198,11 +208,11 @@ itl_directed_kernel(const double* __restrict__ var, const double* __restrict__ c
 template <typename T, int RULE>
 static int launch_colsum_rows(const T* cov, i64 ld, i64 row0, i64 n_loc, i64 N, const i64* roi_idx,
                               i64 m, const double* row_weight, const double* dinv, double p0,
-                              double p1, double* part, int n_split, cudaStream_t st) {
+                              double p1, double* part, int n_split, cudaStream_t st, i64 sym_block) {
   constexpr int VN = Vec16<T>::n;
   dim3 grid((unsigned)((ld + 256 * VN - 1) / (256 * VN)), (unsigned)n_split);
   colsum_rows_kernel<T, RULE, 4><<<grid, 256, 0, st>>>(cov, ld, row0, n_loc, N, roi_idx, m,
-                                                       row_weight, dinv, p0, p1, part);
+                                                       row_weight, dinv, p0, p1, part, sym_block);
   return 0;
 }
 
@@ -221,10 +231,10 @@ int tal_score_itl_undirected(const double* var, const double* rho, int q, long l
   return TAL_OK;
 }
 
-int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+static int colsum_rows_impl(int rule, const void* cov, long long ld, long long row0, long long n_loc,
                     long long N, const long long* roi_idx, long long m, const double* row_weight,
                     const double* dinv, double p0, double p1, double* part, int n_split,
-                    double* c_out, int dtype, void* stream) {
+                    double* c_out, int dtype, void* stream, i64 sym_block) {
   TAL_ARG(cov && roi_idx && part && c_out && m >= 0 && n_split >= 1 && n_split <= 65535);
   TAL_ARG(ld % 32 == 0 && ld >= N);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
@@ -233,7 +243,7 @@ int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, lon
   double* dst = n_split == 1 ? c_out : part;
 #define TAL_ROWS(T, R)                                                                          \
   launch_colsum_rows<T, R>((const T*)cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, \
-                           p1, dst, n_split, st)
+                           p1, dst, n_split, st, sym_block)
   if (dtype == TAL_F64) {
     switch (rule) {
       case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_ROWS(double, TAL_RULE_VTL); break;
@@ -256,10 +266,18 @@ int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, lon
   return TAL_OK;
 }
 
-int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
+int tal_colsum_rows(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                    long long N, const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* part, int n_split,
+                    double* c_out, int dtype, void* stream) {
+  return colsum_rows_impl(rule, cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, p1, part,
+                          n_split, c_out, dtype, stream, 0);
+}
+
+static int colsum_cols_impl(int rule, const void* cov, long long ld, long long n_loc,
                     const long long* roi_idx, long long m, const double* row_weight,
                     const double* dinv, double p0, double p1, double* c_out, int dtype,
-                    void* stream) {
+                    void* stream, i64 sym_block, i64 row0, int accumulate) {
   TAL_ARG(cov && roi_idx && c_out && m >= 0 && n_loc >= 0);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
@@ -268,7 +286,8 @@ int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
   const unsigned grid = (unsigned)((n_loc + 7) / 8);
 #define TAL_COLS(T, R)                                                                        \
   colsum_cols_kernel<T, R><<<grid, 256, 0, st>>>((const T*)cov, ld, n_loc, roi_idx, m,        \
-                                                 row_weight, dinv, p0, p1, c_out)
+                                                 row_weight, dinv, p0, p1, c_out, sym_block,  \
+                                                 row0, accumulate)
   if (dtype == TAL_F64) {
     switch (rule) {
       case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_COLS(double, TAL_RULE_VTL); break;
@@ -285,6 +304,30 @@ int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
 #undef TAL_COLS
   TAL_LAUNCH_CHECK("tal_colsum_cols");
   return TAL_OK;
+}
+
+int tal_colsum_cols(int rule, const void* cov, long long ld, long long n_loc,
+                    const long long* roi_idx, long long m, const double* row_weight,
+                    const double* dinv, double p0, double p1, double* c_out, int dtype,
+                    void* stream) {
+  return colsum_cols_impl(rule, cov, ld, n_loc, roi_idx, m, row_weight, dinv, p0, p1, c_out, dtype,
+                          stream, 0, 0, 0);
+}
+
+/* lower-block storage: c[x] = sum_{a in ROI} elem(cov[a][x]) over ALL x in [0, N), from what this
+ * shard keeps: the kept part of its ROI rows (row reduce) plus, for its own rows x, the ROI entries
+ * mirrored into row x (column gather, accumulated).  Every pair (a, x) is counted exactly once
+ * across the shards; a sum over the shards completes c. */
+int tal_colsum_lower(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                     long long N, const long long* roi_idx, long long m, const double* row_weight,
+                     const double* dinv, double p0, double p1, double* part, int n_split,
+                     double* c_out, int dtype, void* stream) {
+  const i64 blk = tal_sym_block(dtype);
+  int rc = colsum_rows_impl(rule, cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, p1, part,
+                            n_split, c_out, dtype, stream, blk);
+  if (rc != TAL_OK) return rc;
+  return colsum_cols_impl(rule, cov, ld, n_loc, roi_idx, m, row_weight, dinv ? dinv + row0 : nullptr, p0,
+                          p1, c_out + row0, dtype, stream, blk, row0, 1);
 }
 
 int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,

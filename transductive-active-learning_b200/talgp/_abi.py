@@ -65,6 +65,8 @@ SIGNATURES = {
     "tal_score_itl_undirected": (_i, [_p, _p, _i, _ll, _p, _p]),
     "tal_colsum_rows": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p,
                              _i, _p]),
+    "tal_colsum_lower": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p,
+                              _i, _p]),
     "tal_colsum_cols": (_i, [_i, _p, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p]),
     "tal_roi_trace": (_i, [_p, _p, _ll, _p, _p]),
     "tal_roi_weights": (_i, [_p, _p, _ll, _i, _p, _p]),

@@ -247,9 +247,7 @@ class DeviceGP:
         n, d = domain.shape
         assert n == self.N
         if self.q == 1:
-            self._upper_stale = False
-        else:
-            self.ensure_full()
+            self._upper_stale = False  # (with several GPs the flag keeps covering the other ones)
         _abi.check(self.lib.tal_gram_stationary(
             kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
             _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
@@ -269,10 +267,8 @@ class DeviceGP:
     def load_covariance(self, i: int, cov) -> None:
         """Upload a full N x N covariance (host or device) into shard i."""
         src = torch.as_tensor(cov)
-        if self.q > 1:
-            self.ensure_full()
-        else:
-            self._upper_stale = False
+        if self.q == 1:
+            self._upper_stale = False  # (with several GPs the flag keeps covering the other ones)
         rows = src[self.row0:self.row0 + self.n_loc]
         self.cov[i, :, : self.N].copy_(rows.to(device=self.device, dtype=self.dtype))
         self.var[i].copy_(torch.diagonal(src).to(device=self.device, dtype=torch.float64))
@@ -436,7 +432,8 @@ class DeviceGP:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
         lib = self.lib
         N = self.N
-        self.ensure_full()  # the row / column gathers below read entries on both sides of the diagonal
+        if self.lower:
+            return self._score_rows_lower(rule, roi_idx, m, p0, p1)
         sharded_cols = sharded_cols or self.sharded
         n_out = self.n_loc if sharded_cols else N
         off = self.row0 if sharded_cols else 0
@@ -478,6 +475,49 @@ class DeviceGP:
                                              _stream()), "tal_roi_trace")
             _abi.check(lib.tal_score_rows_finish(
                 rule, _ptr(c), _ptr(self.var[i, off:]), _ptr(self.rho[i, off:]), _ptr(tr), n_out,
+                1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
+        return F
+
+    def _score_rows_lower(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0) -> torch.Tensor:
+        """The row-reduce rules in lower-block storage: every pair (a, x) of a target point and a
+        candidate is kept either in row a (x below the end of a's diagonal block) or in row x;
+        `tal_colsum_lower` sums what this shard keeps over all N candidates, a sum over the shards
+        completes the vector, and every rank finishes its own candidates."""
+        lib, N = self.lib, self.N
+        n_out, off = self.n_cand, self.cand0
+        F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
+        if m == 0:
+            F.zero_()
+            if rule == _abi.RULE_VTL:
+                F.neg_()
+            return F
+        c = self._scratch("score_c_full", (N,))
+        tr = self._scratch("score_tr", (1,))
+        need_w = rule != _abi.RULE_VTL
+        need_dinv = rule in (_abi.RULE_MMITL, _abi.RULE_TRUVAR)
+        w = self._scratch("score_w", (max(m, 1),)) if need_w else None
+        dinv = self._scratch("score_dinv", (N,)) if need_dinv else None
+        n_split = self._n_split(m)
+        part = self._scratch("score_part", (n_split, N))
+        for i in range(self.q):
+            if need_w:
+                _abi.check(lib.tal_roi_weights(_ptr(self.var[i]), _ptr(roi_idx), m,
+                                               0 if rule == _abi.RULE_TRUVAR else 1, _ptr(w),
+                                               _stream()), "tal_roi_weights")
+            if need_dinv:
+                _abi.check(lib.tal_pred_var_inv(_ptr(self.var[i]), _ptr(self.rho[i]), N,
+                                                _ptr(dinv), _stream()), "tal_pred_var_inv")
+            pp0 = float(p0[i]) if p0 is not None else 0.0
+            _abi.check(lib.tal_colsum_lower(
+                rule, _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(w),
+                _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt, _stream()),
+                "tal_colsum_lower")
+            self._sum(c)
+            if rule == _abi.RULE_VTL:
+                _abi.check(lib.tal_roi_trace(_ptr(self.var[i]), _ptr(roi_idx), m, _ptr(tr),
+                                             _stream()), "tal_roi_trace")
+            _abi.check(lib.tal_score_rows_finish(
+                rule, _ptr(c[off:]), _ptr(self.var[i, off:]), _ptr(self.rho[i, off:]), _ptr(tr), n_out,
                 1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
         return F
 
