@@ -24,6 +24,8 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = [
+    "TruVar",
+    "TruVarModel",
     "ContinuousModel",
     "LineBO",
     "UnknownFunction",
@@ -884,3 +886,31 @@ def thompson_masks_from_samples(samples, I, J):
         masks.append(safety & optimality)
         values.append(safe_optimum)
     return np.array(masks), np.array(values)
+
+
+# --------------------------------------------------------------------------- #
+# TruVar (lib/algorithms/tru_var/__init__.py:10-50, model.py:8-33)
+# --------------------------------------------------------------------------- #
+class TruVarModel(MarginalModel):
+    def __init__(self, eta, delta, r, **kwargs):
+        super().__init__(**kwargs)
+        self.eta, self.delta, self.r = eta, delta, r
+
+    def update_variance_threshold(self, roi):  # model.py:28-33
+        idx = self.get_indices(roi)
+        if np.all(np.sqrt(self.beta(self.t)[0]) * self.stddevs[:, idx] <= (1 + self.delta) * self.eta):
+            self.eta = self.r * self.eta
+
+
+class TruVar(DirectedDiscreteGreedyAlgorithm):
+    def F(self):  # __init__.py:17-50
+        assert self.model.q == 1 and self.model.first_constraint == 1
+        roi = self.roi
+        self.model.update_variance_threshold(roi)
+        beta = self.model.beta(self.model.t)[0]
+        covariance = self.model.covariances[0]
+        variance = self.model.variances[0]
+        noise_var = np.square(self.model.noise_rate.at(self.model.domain)[0])
+        idx = get_indices(self.model.domain, roi)
+        post = variance[idx][:, None] - covariance[idx, :] ** 2 / (variance + noise_var)[None, :]  # [m, n]
+        return -np.sum(np.maximum(beta * post, self.model.eta ** 2), axis=0)

@@ -298,6 +298,31 @@ def next_rows():
         out[f"linebo/{t}/subspace_bounds"] = np.array([float(b) for b in lbo.subspace_bounds()])
     out["linebo/final_X"], out["linebo/final_y"] = np.asarray(lm.X), np.asarray(lm.y)
     out["linebo/encountered_max"] = np.asarray(lbo.encountered_max)
+    # ---- TruVar with a fixed ROI (lib/algorithms/tru_var/__init__.py, model.py)
+    from lib.algorithms.tru_var import TruVar
+    from lib.algorithms.tru_var.model import TruVarModel
+    import problems as P
+    p3 = P.c3(T=8)
+    dom3 = jnp.array(p3["domain"])
+    nz = HomoscedasticNoise(1, jnp.array(p3["rho"]))
+    d3 = prior_distr(nz, dom3, jnp.array(p3["X0"]), jnp.array(p3["y0"]),
+                     [stationary.Matern52(variance=1.0, lengthscale=0.25)], [ZeroMean()])
+    tv = TruVarModel(eta=1.2, delta=0.3, r=0.5, key=jr.PRNGKey(4), domain=dom3, distrs=d3, beta=jnp.array([2.0]),
+                     noise_rate=nz)
+    A3 = np.asarray(p3["roi"])
+    alg = TruVar(tv, lambda m: m.domain[A3])
+    ftab = TableFunction(dom3, p3["table"], tv.first_constraint)
+    Fs, sels, etas = [], [], []
+    for t in range(8):
+        F = alg.F()
+        etas.append(float(tv.eta))
+        safe_F = np.asarray(F)
+        idx = int(np.flatnonzero(safe_F == np.nanmax(safe_F))[0])
+        Fs.append(np.asarray(F)); sels.append(idx)
+        X = tv.domain[idx: idx + 1]
+        tv.step(X=X, y=ftab.observe(X))
+    out["truvar/F"], out["truvar/sel"], out["truvar/eta"] = np.array(Fs), np.array(sels), np.array(etas)
+    out["truvar/means"], out["truvar/variances"] = np.asarray(tv.means), np.asarray(tv.variances)
     # ---- Thompson-sampling masks on preset samples (marginal.py:238-312)
     N, q, k = 30, 3, 6
     dom = rng.random((N, 2))

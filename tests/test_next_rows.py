@@ -242,3 +242,45 @@ def test_reference_test_line_bo(cuda):
     kw = dict(alg=alg_constructor(DummyAlg), model=model, bounds=bounds, n=10, eps=0.01)
     for lbo in (RandomLineBO(**kw), CoordinateLineBO(**kw), DescentLineBO(m=2 * D, alpha=0.1, **kw)):
         assert float(torch.linalg.norm(lbo._normalized_direction(f))) == pytest.approx(1, abs=1e-5)
+
+
+def test_truvar_matches_reference(be):
+    """TruVar (lib/algorithms/tru_var/__init__.py:17-50) with TruVarModel's shrinking
+    variance threshold (model.py:28-33) on the fixed-ROI problem c3: F, eta and the selections over
+    8 steps, teacher-forced."""
+    import problems
+    p = problems.c3(T=8)
+    A = np.asarray(p["roi"])
+    if isinstance(be, OracleBE):
+        O = be.O
+        nz = O.HomoscedasticNoise(1, np.asarray(p["rho"]))
+        distrs = O.prior_distr(nz, p["domain"], p["X0"], p["y0"], [O.Matern52(variance=1.0, lengthscale=0.25)],
+                               [O.ZeroMean()])
+        model = O.TruVarModel(eta=1.2, delta=0.3, r=0.5, key=4, domain=p["domain"], distrs=distrs,
+                              beta=np.array([2.0]), noise_rate=nz)
+        alg = O.TruVar(model, lambda m: m.domain[A])
+        f = O.TableFunction(p["domain"], p["table"])
+    else:
+        from lib.algorithms import index_roi_constructor
+        from lib.algorithms.tru_var import TruVar
+        from lib.algorithms.tru_var.model import TruVarModel
+        from lib.function import TableFunction
+        from lib.gp.means import ZeroMean
+        from lib.gp.prior import prior_distr
+        nz = be.HomoscedasticNoise(1, np.asarray(p["rho"]))
+        distrs = prior_distr(nz, p["domain"], p["X0"], p["y0"], [be.kernel("Matern52", variance=1.0, lengthscale=0.25)],
+                             [ZeroMean()])
+        model = TruVarModel(eta=1.2, delta=0.3, r=0.5, key=4, domain=p["domain"], distrs=distrs,
+                            beta=np.array([2.0]), noise_rate=nz)
+        alg = TruVar(model, index_roi_constructor(A))
+        f = TableFunction(model.domain, p["table"])
+    for t in range(8):
+        F = be.np(alg.F())
+        assert float(model.eta) == pytest.approx(float(NEXT["truvar/eta"][t]), rel=1e-12)
+        np.testing.assert_allclose(F, NEXT["truvar/F"][t], rtol=1e-10, atol=1e-12)
+        idx = int(NEXT["truvar/sel"][t])
+        assert F[idx] >= F.max() - 1e-9 * max(1.0, abs(F.max()))
+        X = model.domain[idx: idx + 1]
+        model.step(X, f.observe(X))
+    np.testing.assert_allclose(be.np(model.means), NEXT["truvar/means"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(be.np(model.variances), NEXT["truvar/variances"], rtol=1e-10, atol=1e-12)
