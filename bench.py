@@ -228,8 +228,9 @@ def recompute_kernels(gp, roi, hbm_peak):
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
     def gather():
-        _abi.check(lib.tal_gather_roi(p(gp.cov[0]), gp.ld, gp.N, p(roi.idx), roi.m, m_pad, 1e-5, p(S), m_pad,
-                                      p(B), ncols, gp.dt, stream))
+        fn = lib.tal_gather_roi_lower if gp.lower else lib.tal_gather_roi
+        _abi.check(fn(p(gp.cov[0]), gp.ld, gp.N, p(roi.idx), roi.m, m_pad, 1e-5, p(S), m_pad,
+                      p(B), ncols, gp.dt, stream))
     def potrf():
         gather()
         _abi.check(lib.tal_potrf_lower(p(S), m_pad, m_pad, p(work), stream))

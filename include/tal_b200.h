@@ -282,6 +282,10 @@ int tal_gather_roi(const void* cov, long long ld, long long N, const long long* 
  * entry cov_loc[x][roi[j]] ([m_pad][ldb], ncols >= n_loc columns written, pads
  * zero); S receives the rows whose roi[j] this shard owns (+ the identity pad
  * on the shard with row0 = 0) and zeros elsewhere: a sum over shards gives S. */
+/* lower-block storage, one GPU holding all rows: the same gather through the mirrored entries. */
+int tal_gather_roi_lower(const void* cov, long long ld, long long N, const long long* roi_idx,
+                         long long m, long long m_pad, double jitter, double* S, long long lds,
+                         double* B, long long ldb, int dtype, void* stream);
 int tal_gather_roi_sharded(const void* cov, long long ld, long long row0, long long n_loc,
                            const long long* roi_idx, long long m, long long m_pad, double jitter,
                            double* S, long long lds, double* B, long long ldb, long long ncols,

@@ -34,6 +34,23 @@ gather_roi_B_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restr
   B[j * ldb + col] = v;
 }
 
+// lower-block storage (one GPU holding all rows): entry (a, col) beyond the end of a's diagonal
+// block is read from its mirror image (col, a)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_roi_B_lower_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restrict__ roi_idx,
+                          i64 m, double* __restrict__ B, i64 ldb, i64 sym_block) {
+  const i64 j = blockIdx.y;
+  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ldb) return;
+  double v = 0.0;
+  if (j < m && col < N) {
+    const i64 a = roi_idx[j];
+    v = col < (a / sym_block + 1) * sym_block ? (double)cov[a * ld + col] : (double)cov[col * ld + a];
+  }
+  B[j * ldb + col] = v;
+}
+
 __global__ void __launch_bounds__(256)
 gather_roi_S_kernel(const double* __restrict__ B, i64 ldb, const i64* __restrict__ roi_idx, i64 m,
                     i64 m_pad, double jitter, double* __restrict__ S, i64 lds) {
@@ -488,6 +505,26 @@ int tal_gather_roi(const void* cov, long long ld, long long N, const long long* 
   dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
   gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
   TAL_LAUNCH_CHECK("tal_gather_roi/S");
+  return TAL_OK;
+}
+
+int tal_gather_roi_lower(const void* cov, long long ld, long long N, const long long* roi_idx,
+                         long long m, long long m_pad, double jitter, double* S, long long lds,
+                         double* B, long long ldb, int dtype, void* stream) {
+  TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
+  TAL_ARG(lds >= m_pad && ldb >= N && m_pad <= 65535);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  cudaStream_t st = as_stream(stream);
+  const i64 blk = tal_sym_block(dtype);
+  dim3 gb((unsigned)((ldb + 255) / 256), (unsigned)m_pad);
+  if (dtype == TAL_F64)
+    gather_roi_B_lower_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, N, roi_idx, m, B, ldb, blk);
+  else
+    gather_roi_B_lower_kernel<float><<<gb, 256, 0, st>>>((const float*)cov, ld, N, roi_idx, m, B, ldb, blk);
+  TAL_LAUNCH_CHECK("tal_gather_roi_lower/B");
+  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
+  TAL_LAUNCH_CHECK("tal_gather_roi_lower/S");
   return TAL_OK;
 }
 

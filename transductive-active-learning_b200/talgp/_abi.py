@@ -73,6 +73,7 @@ SIGNATURES = {
     "tal_pred_var_inv": (_i, [_p, _p, _ll, _p, _p]),
     "tal_score_rows_finish": (_i, [_i, _p, _p, _p, _p, _ll, _i, _p, _p]),
     "tal_gather_roi": (_i, [_p, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _i, _p]),
+    "tal_gather_roi_lower": (_i, [_p, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _i, _p]),
     "tal_gather_roi_sharded": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _d, _p, _ll, _p, _ll, _ll, _i, _p]),
     "tal_potrf_work_bytes": (_ll, [_ll]),
     "tal_potrf_lower": (_i, [_p, _ll, _ll, _p, _p]),

@@ -542,8 +542,8 @@ class DeviceGP:
         if self.lower and self.comm is not None:
             self._gather_roi_lower_sharded(i, roi_idx, m, m_pad, ncols, jitter, S, B)
         elif self.comm is None:
-            self.ensure_full()
-            _abi.check(lib.tal_gather_roi(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m,
+            gather = lib.tal_gather_roi_lower if self.lower else lib.tal_gather_roi
+            _abi.check(gather(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m,
                                           m_pad, float(jitter), _ptr(S), m_pad, _ptr(B), ldb,
                                           self.dt, _stream()), "tal_gather_roi")
         else:
