@@ -266,6 +266,7 @@ def workload_config(args, w, world):
                      f"(l={w['lengthscale']}), q=1, rho={w['rho']}, {'fp32' if getattr(args, 'dtype', 'f64') == 'f32' else 'fp64'}"),
         "name": args.workload, "N": w["N"], "m": w["m"], "d": w["d"], "q": 1,
         "conditioning": args.conditioning,
+        "update_block": int(os.environ.get("TAL_UPDATE_BLOCK", "16")),
         "storage": ("full N x N covariance (reference layout)" if args.storage == "full" else
                     "lower-block: only the blocks on or below the diagonal are maintained (symmetric matrix)"),
         "l2": "inputs larger than L2 (covariance %.1f GB per GPU >> 126 MB): no flush needed"
@@ -349,31 +350,34 @@ def run_ours(args, w):
         inc = args.conditioning == "incremental"
 
         # ---- device-resident loop (value) -----------------------------------
-        ev, ev_cond = [], []
+        ev = []
+
+        import ctypes as C
+        sample = alg.sample_mask()
+        use_ctx = inc and gp._ctx_usable()
 
         def dev_step(record):
+            """One step with index, observation table and state on the device.  Incremental mode: the
+            whole launch sequence is ONE host call (tal_ctx_step, csrc/stepctx.cu); the first step (and a
+            step after the conditioning factor filled up) conditions on the target set from scratch."""
+            st = gp._cond
+            if use_ctx and st is not None and st["valid"]:
+                gp.ctx_step(table_dev, N, beta, model.first_constraint, None, sample)
+                return
             F = gp.score_itl_directed(roi.idx, roi.m, incremental=inc, roi_key=roi)
-            res = gp.masked_argmax(F, None, model.first_constraint, alg.sample_mask())
-            idx_dev = res[0:1]  # tal_argmax_result.idx
-            gp.extract_row(idx_dev)
-            gp.step_vectors(idx_dev, 0, table_dev, N, True, beta)
-            if gp._cond is not None and gp._cond["valid"]:
-                if record:
-                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    c0.record()
-                    gp._cond_downdate(idx_dev, 0)
-                    c1.record()
-                    ev_cond.append((c0, c1))
-                else:
-                    gp._cond_downdate(idx_dev, 0)
-            if record:
+            res = gp.masked_argmax(F, None, model.first_constraint, sample)
+            if record and not use_ctx:  # recompute mode: time the pass with events around the update
+                idx_dev = res[0:1]
+                gp.exchange_row(idx_dev)
+                gp.step_vectors(idx_dev, 0, table_dev, N, True, beta)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                gp.rank1_update()
+                passed = gp.rank1_update()
                 e1.record()
-                ev.append((e0, e1))
+                if passed:
+                    ev.append((e0, e1))
             else:
-                gp.rank1_update()
+                gp.observe(res[0:1], table_dev, beta, y_gather=True, y_stride=N)
 
         clocks.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
         for _ in range(args.warmup):
@@ -381,15 +385,57 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         l_start, u_start = gp.l.clone(), gp.u.clone()
         lib.tal_reset_launch_count()
+        ctx = gp._ctx_get() if use_ctx else None
+        if ctx is not None:
+            lib.tal_ctx_timing_begin(C.byref(ctx))  # CUDA events around every pass over the matrix
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):
             dev_step(True)
+        if ctx is not None:  # the updates still pending are applied inside the timed region
+            ctx.pending = gp._pending
+            _abi.check(lib.tal_ctx_flush(C.byref(ctx), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            gp._ctx_done(ctx)
+        elif gp._pending:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gp.flush(); e1.record()
+            ev.append((e0, e1))
         t1.record()
         torch.cuda.synchronize()
         total_ms = t0.elapsed_time(t1)
         launches = int(lib.tal_launch_count())
-        rank1_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        if ctx is not None:
+            ms_buf, n_buf = (C.c_double * 64)(), C.c_longlong(0)
+            _abi.check(lib.tal_ctx_timing_read(C.byref(ctx), ms_buf, C.byref(n_buf),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            pass_ms = [float(ms_buf[i]) for i in range(int(n_buf.value))]
+        else:
+            pass_ms = [a.elapsed_time(b) for a, b in ev]
+        ev = pass_ms
+        rank1_ms = float(np.mean(pass_ms))
+        rank1_total_ms = float(np.sum(pass_ms))
+        # the scoring pass (conditioning update), timed after the loop on a scratch copy of cs
+        cond_ms = None
+        if inc and gp._cond is not None and gp._cond["valid"] and gp._cond["append"]:
+            st = gp._cond
+            p_ = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+            cs_tmp = st["cs"].clone()
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            idx_dev = gp.argmax_record()[0:1]
+
+            def cond_once():
+                _abi.check(lib.tal_cond_extract_col(p_(st["V"][0]), st["ncols"], st["rows"], gp.cand0, gp.n_cand,
+                                                    p_(idx_dev), 0, p_(st["pcol"]), stream))
+                _abi.check(lib.tal_cond_append_update(
+                    p_(st["V"][0]), st["ncols"], st["cap"], st["m_pad"], st["rows"], st["ncols"], gp.n_cand, gp.cand0,
+                    p_(st["pcol"]), p_(gp.kbuf[0]), p_(gp.wbuf[0]), p_(gp.rho[0]), p_(idx_dev), 0, p_(cs_tmp[0]),
+                    p_(st["app"]), st["n_split"], gp.dt, stream))
+            ts = []
+            for _ in range(6):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(); cond_once(); c1.record(); torch.cuda.synchronize()
+                ts.append(c0.elapsed_time(c1))
+            cond_ms = float(np.median(ts[1:]))
         status = gp.read_result().status
         assert status == 0, f"arg-max status {status}"
         # size-independent invariants of the state after the timed steps (full size, no oracle needed)
@@ -421,6 +467,7 @@ def run_ours(args, w):
         a0.record()
         for _ in range(e2e_steps):
             out = alg.step(f)
+        gp.flush()
         fmax = float(out["F_max"])  # D2H read of the step's result
         a1.record()
         torch.cuda.synchronize()
@@ -442,13 +489,17 @@ def run_ours(args, w):
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches, "invariants": invariants,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-            "roofline": {"kernel": "rank1_update (tal_rank1_update%s)" % ("_lower" if args.storage == "lower" else ""),
+            "roofline": {"kernel": ("rank1_update (tal_rank1_update%s)" % ("_lower" if args.storage == "lower" else "")
+                                    if gp.update_block == 1 else
+                                    "rank-b update: %d deferred rank-1 updates per pass (tal_rankb_update, %s storage)"
+                                    % (gp.update_block, args.storage)),
                          "bound": "hbm", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": peak_src,
-                         "traffic": ncu_traffic("rank1_", args.workload, 1, args.storage),
+                         "traffic": ncu_traffic("rank1_" if gp.update_block == 1 else "rankb_", args.workload, 1, args.storage),
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": rank1_ms,
-                         "share_of_step": rank1_ms / (total_ms / args.steps),
+                         "launches_in_timed_region": len(ev), "updates_per_launch": gp.update_block,
+                         "share_of_step": rank1_total_ms / total_ms,
                          "frac_of_8TBs_datasheet": achieved / 8000.0,
                          "effective_GBs_vs_full_matrix_bytes": 2.0 * model.q * N * N * (4 if args.dtype == "f32" else 8)
                                                                / (rank1_ms * 1e-3) / 1e9},
@@ -456,27 +507,25 @@ def run_ours(args, w):
         # the scoring pass of this mode next to the dominant kernel (north_star: HBM GB/s of the
         # rank-1 update AND the scoring pass; tensor-pipe utilisation of the TRSM in recompute mode)
         line["kernels"] = []
-        if ev_cond:
+        if cond_ms is not None:
             st = gp._cond
-            cond_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_cond]))
-            if st["append"]:  # one read of the factor (rows in use, mid-run) + two appended rows
-                cbytes = model.q * (st["rows"] - args.steps + 2.0) * st["ncols"] * 8
-                kname = "cond_append_update (incremental target-set conditioning = the ITL scoring pass; read-only GEMV over the factor)"
-            else:
-                cbytes = 2.0 * model.q * st["m_pad"] * st["ncols"] * 8
-                kname = "cond_update (incremental target-set conditioning = the ITL scoring pass; rewrites V)"
+            cbytes = model.q * (st["rows"] + 2.0) * st["ncols"] * 8  # one read of the factor + two appended rows
             line["kernels"].append({
-                "kernel": kname,
+                "kernel": "cond_append_update (incremental target-set conditioning = the ITL scoring pass; "
+                          "read-only GEMV over the factor)",
                 "bound": "hbm", "achieved": cbytes / (cond_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": cbytes / (cond_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": cbytes,
-                "ms_per_launch": cond_ms, "traffic": ncu_traffic("cond_app_partial" if st["append"] else "cond_update", args.workload, 1, args.storage),
-                "share_of_step": cond_ms / (total_ms / args.steps)})
+                "ms_per_launch": cond_ms, "launches_per_step": 1,
+                "traffic": ncu_traffic("cond_app_partial", args.workload, 1, args.storage),
+                "share_of_step": cond_ms / (total_ms / args.steps),
+                "timed": "after the loop, CUDA events, same buffers (scratch copy of cs)"})
         if not inc:
             line["kernels"] += recompute_kernels(gp, roi, hbm_peak)
         # beside the headline: the reference-style variants of the same workload, each a sub-run
         #   value_recompute     re-conditioning on the target set from scratch at every step (as the reference)
         #   value_full_storage  the full N x N covariance maintained (the reference's layout)
         if args.both:
+            gp_update_block = gp.update_block
             del model, alg, gp, roi
             torch.cuda.empty_cache()
             variants = []
@@ -486,6 +535,9 @@ def run_ours(args, w):
                 variants.append(("value_incremental", ["--conditioning", "incremental", "--storage", args.storage]))
             if args.storage == "lower":
                 variants.append(("value_full_storage", ["--conditioning", args.conditioning, "--storage", "full"]))
+            if gp_update_block > 1:
+                variants.append(("value_update_every_step", ["--conditioning", args.conditioning, "--storage",
+                                                             args.storage, "--update-block", "1"]))
             if args.dtype == "f64":
                 variants.append(("value_fp32_storage", ["--conditioning", args.conditioning, "--storage", args.storage,
                                                         "--dtype", "f32"]))
@@ -520,13 +572,16 @@ def run_ours(args, w):
     torch.cuda.synchronize()
     dist.barrier()
     lib.tal_reset_launch_count()
+    bench.timing_begin()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
     for _ in range(args.steps):
         bench.step(True)
+    bench.flush(True)  # the updates still pending are applied inside the timed region
     t1.record()
     torch.cuda.synchronize()
+    bench.timing_end()
     dist.barrier()
     total_ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
     dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -577,12 +632,16 @@ def run_ours(args, w):
                     "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "invariants": invariants,
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-            "roofline": {"kernel": "rank1_update (tal_rank1_update%s), per GPU, max over ranks" % (
-                "_lower" if args.storage == "lower" else ""), "bound": "hbm",
+            "roofline": {"kernel": ("rank1_update (tal_rank1_update%s), per GPU, max over ranks" % (
+                "_lower" if args.storage == "lower" else "") if bench.gp.update_block == 1 else
+                "rank-b update: %d deferred rank-1 updates per pass (tal_rankb_update, %s storage), per GPU, "
+                "max over ranks" % (bench.gp.update_block, args.storage)), "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": peak_src, "traffic": ncu_traffic("rank1_", args.workload, world, args.storage),
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "ms_per_launch": rank1_ms, "share_of_step": rank1_ms / (total_ms / args.steps),
+                         "ms_per_launch": rank1_ms, "updates_per_launch": bench.gp.update_block,
+                         "launches_in_timed_region": len(bench.pass_ms),
+                         "share_of_step": rank1_ms * len(bench.pass_ms) / total_ms,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
         }
         print(json.dumps(line), flush=True)
@@ -600,6 +659,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--storage", default=os.environ.get("TAL_STORAGE", "lower"), choices=["full", "lower"],
                     help="covariance storage: full N x N (reference layout) or lower-block (symmetric)")
+    ap.add_argument("--update-block", type=int, default=None,
+                    help="covariance updates applied per pass over the matrix (default 16; 1 = after every observation)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="covariance storage / arithmetic type (the reference's only mode is f64)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
@@ -607,6 +668,8 @@ def main():
     ap.add_argument("--no-both", dest="both", action="store_false",
                     help="do not also time the other conditioning mode")
     args = ap.parse_args()
+    if args.update_block is not None:
+        os.environ["TAL_UPDATE_BLOCK"] = str(args.update_block)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -165,6 +165,27 @@ int tal_rankm_update_lower(void* cov, long long ld, long long row0, long long n_
 int tal_sym_mirror(void* cov, long long cov_stride_q, long long ld, long long N, int q, int dtype,
                    void* stream);
 
+/* ---- temporally blocked posterior update ------------------------------------
+ * The (k_i, w_i) of the last p <= TAL_MAX_PENDING observations may be kept pending
+ * (K, W: [p][q][ld] of the cov dtype, `pend_stride` elements between slots, unused
+ * slots zero) instead of streaming the matrix after every one of them:
+ * tal_pending_correct_row applies them to the row that the next observation reads
+ *   (kbuf [q][ld] as written by tal_extract_row[_lower] / the peer exchange):
+ *   k[c] <- ((k[c] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ... with (a, b) = (idx, c), or
+ *   (c, idx) for the mirrored entries of lower-block storage;
+ * tal_rankb_update applies all p of them to every maintained entry in ONE pass:
+ *   cov[a][b] <- ((cov[a][b] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ...
+ * Each entry sees the same sequence of rounded operations as p calls of
+ * tal_rank1_update[_lower]: the result is bit-identical, the HBM traffic per
+ * observation is divided by p (the pass stays HBM-bound up to p = 16).            */
+#define TAL_MAX_PENDING 16
+int tal_rankb_update(void* cov, long long cov_stride_q, long long ld, long long row0, long long n_loc,
+                     long long N, int q, const void* K, const void* W, long long pend_stride, int p,
+                     int lower, int dtype, void* stream);
+int tal_pending_correct_row(void* kbuf, long long ld, long long N, int q, const void* K, const void* W,
+                            long long pend_stride, int p, const long long* idx_dev, long long idx_host,
+                            int lower, int dtype, void* stream);
+
 /* ---- posterior update, m observations ---------------------------------
  * Replaces GaussianDistribution.posterior for general m (prior_distr,
  * lib/gp/prior.py:52-66; SafeOpt/GoOSE replay).  One GP per call.
@@ -416,6 +437,61 @@ int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* 
 int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,
                       long long N, int q, double* scal, void* stream);
 int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synchronises */
+
+/* ---- one BO step as one host call -------------------------------------------
+ * The per-step launch sequence of the greedy loop (lib/algorithms/__init__.py:77-94
+ * with the directed-ITL rule over a resident conditioning state) issued from a
+ * context that the host fills once: every field is 8 bytes wide (pointers, long
+ * long, double), device pointers unless noted.  The functions only call the entry
+ * points above; the counters `pending`, `rows`, `passes`, `n_ev` are advanced here
+ * and read back by the host.
+ *   tal_ctx_select   F = directed-ITL score of this rank's candidates from (var, cs, rho);
+ *                    masked arg-max into `combined` (sharded: into `rec`, then the peer
+ *                    all-gather + combine).
+ *   tal_ctx_observe  row idx into kbuf (extract, or the peer exchange incl. the
+ *                    conditioning column), pending-row correction, step vectors, the
+ *                    append-form conditioning update of every GP (if cond_valid), then
+ *                    the covariance update: queued, and applied to the matrix in one
+ *                    pass every `update_block` observations (update_block = 1: at once).
+ *                    Returns TAL_CTX_REBASE (nothing enqueued) when the conditioning
+ *                    factor is full: the host re-conditions from scratch.
+ *   tal_ctx_step     select + observe with y taken from y_table[i][idx].
+ *   tal_ctx_flush    applies the pending updates now.
+ *   tal_ctx_timing_begin / _read: CUDA events around every pass over the matrix
+ *                    (read synchronises the stream): the kernel times bench.py reports. */
+#define TAL_CTX_REBASE 6
+#define TAL_CTX_MAX_EVENTS 64
+typedef struct tal_step_ctx {
+  /* model */
+  void* cov; long long cov_stride_q, ld, row0, n_loc, N, q, dtype, lower;
+  double *mean, *var, *l, *u, *rho, *scal;
+  void *kbuf, *wbuf;
+  double beta[TAL_MAX_Q];            /* host values */
+  /* deferred covariance updates */
+  void *Kp, *Wp; long long pend_stride, pend_slots, update_block, pending, passes;
+  /* incremental conditioning, append form (Wb null: none) */
+  double* Wb; long long ldw, cap_rows, m_pad, rows, ncols, cand0, n_cand, n_split, cond_valid;
+  double *cs, *app_scratch, *pcol;
+  /* selection */
+  double* F; const unsigned char *safe, *sample; long long first_constraint;
+  void* argmax_scratch; tal_argmax_result *rec, *combined;
+  /* observations for tal_ctx_step */
+  const double* y_table; long long y_stride;
+  /* row-sharded model over peer memory (G == 1: unused) */
+  void* const* mailboxes; void* mailbox; long long G, rank;
+  long long bounds[TAL_PEER_MAX + 1]; /* host values */
+  long long kbuf_off, pcol_off; const double* pcol_peer; long long pcol_stride;
+  /* pass timing (host handles) */
+  void* ev_start[TAL_CTX_MAX_EVENTS]; void* ev_stop[TAL_CTX_MAX_EVENTS]; long long n_ev, timing;
+} tal_step_ctx;
+long long tal_step_ctx_bytes(void);
+int tal_ctx_select(tal_step_ctx* ctx, void* stream);
+int tal_ctx_observe(tal_step_ctx* ctx, const long long* idx_dev, long long idx_host, const double* y_dev,
+                    long long y_stride, int y_gather, void* stream);
+int tal_ctx_step(tal_step_ctx* ctx, void* stream);
+int tal_ctx_flush(tal_step_ctx* ctx, void* stream);
+int tal_ctx_timing_begin(tal_step_ctx* ctx);
+int tal_ctx_timing_read(tal_step_ctx* ctx, double* ms_out_host, long long* n_out_host, void* stream);
 
 /* ---- fp64 peak probes (roofline denominators of the tensor path) --------
  * kind 0: DMMA.8x8x4, kind 1: DFMA; `blocks` CTAs x 256 threads x iters x 16

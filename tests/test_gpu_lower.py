@@ -50,6 +50,7 @@ def test_rank1_lower_matches_full(cuda, dtype, N):
     for name in ("mean", "var", "l", "u"):
         torch.testing.assert_close(getattr(low, name), getattr(full, name), **tol)
     # the kept blocks carry the diagonal: var == diag(cov) bit for bit, as in full storage
+    low.flush()  # (updates may still be pending: they are applied in blocks)
     assert low._upper_stale
     for i in range(q):
         assert torch.equal(torch.diagonal(low.cov[i, :, :N]).to(torch.float64), low.var[i])
@@ -117,6 +118,7 @@ def test_lower_storage_matches_reference_trajectories(cuda, name, rule):
     for attr in ("means", "variances", "l", "u"):
         np.testing.assert_allclose(getattr(model, attr).cpu().numpy(), TRAJ[f"{tag}/{attr}"], err_msg=attr,
                                    rtol=1e-10, atol=1e-11)
+    model._gp.flush()
     assert model._gp._upper_stale  # no scoring rule needed the mirrored blocks
     cov = model.covariances
     torch.testing.assert_close(torch.diagonal(cov, dim1=1, dim2=2), model.variances, rtol=0, atol=0)

@@ -14,6 +14,13 @@ pytestmark = pytest.mark.gpu
 
 def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="thread", storage="full"):
     from talgp.dist import LocalPeerComm, ShardedITLBench, ThreadComm
+    if exchange == "peer":
+        # the shards' kernels wait on each other while they share ONE GPU here: a cudaFree issued by the
+        # caching allocator (device-wide synchronisation) in one thread would stall against a spinning
+        # kernel of the other until its time-out, so start from an empty cache (allocations then map
+        # fresh memory, which does not synchronise).  Between processes on separate GPUs this cannot occur.
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
     shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
     out = [None] * G
     errs = []

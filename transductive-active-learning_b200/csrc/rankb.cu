@@ -1,0 +1,194 @@
+// Temporally blocked posterior update: b rank-1 updates applied in ONE pass.
+//
+// Reference path: MarginalModel.step (lib/model/marginal.py:350-368) rewrites the
+// N x N covariance after every observation, Sigma' = Sigma - k^T w
+// (lib/gp/gaussian_distribution.py:36): 2 N^2 s bytes of HBM traffic per step for
+// 2 N^2 flops.  The updates of consecutive steps commute with everything a step
+// reads except the ONE row it observes, so they can be deferred: the (k_i, w_i) of
+// the last p <= b observations are kept ("pending"), the observed row of a new
+// step is read from the not-yet-updated matrix and corrected on the fly,
+//
+//   Sigma_t[x, c] = ((Sigma_base[x, c] - k_0[x] w_0[c]) - k_1[x] w_1[c]) - ...
+//
+// (tal_pending_correct_row; O(p N) work), and after b observations all of them are
+// applied to every entry in one streaming pass (tal_rankb_update): the matrix
+// traffic per step drops by b while each entry sees exactly the same sequence of
+// rounded operations c <- c - rn(k_i[row] * w_i[col]) as b separate rank-1 passes:
+// the result is bit-identical.  The pass stays HBM-bound up to b ~ 16
+// (2 b flops per 16 bytes against 33.8 TFLOP/s of fp64 FMA issue).
+#include "common.cuh"
+
+namespace tal {
+
+__device__ __forceinline__ i64 symb_cend(i64 grow, i64 block, i64 ld) {
+  const i64 e = (grow / block + 1) * block;
+  return e < ld ? e : ld;
+}
+
+template <typename T>
+struct VecB;  // 16-byte vectors: P of them stay in registers per thread
+template <>
+struct VecB<double> {
+  typedef double2 type;
+  static constexpr int n = 2;
+};
+template <>
+struct VecB<float> {
+  typedef float4 type;
+  static constexpr int n = 4;
+};
+
+template <typename T, int VN>
+struct Lanes {
+  T v[VN];
+};
+
+// grid: full storage (row blocks, column tiles, q); lower storage (column tiles, row blocks, q).
+// K, W: [P][q][ld] pending vectors (zero-padded beyond the p in use).  ROWS rows per CTA; the
+// CTA's K values are staged in shared memory ([P][ROWS]), every thread keeps its P w-vectors in
+// registers and has UNROLL rows of loads in flight.
+template <typename T, int P, int UNROLL>
+__global__ void __launch_bounds__(256, 2)
+rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, const T* __restrict__ K,
+             const T* __restrict__ W, i64 pend_stride, int rows_per_cta, i64 sym_block) {
+  typedef typename VecB<T>::type V;
+  constexpr int VN = VecB<T>::n;
+  __shared__ T ksm[P][64];
+  const int gp = blockIdx.z;
+  const i64 rb = sym_block > 0 ? blockIdx.y : blockIdx.x;
+  const i64 ct = sym_block > 0 ? blockIdx.x : blockIdx.y;
+  const i64 col = (ct * 256 + threadIdx.x) * VN;
+  const i64 r0 = rb * rows_per_cta;
+  const i64 r1 = min(n_loc, r0 + (i64)rows_per_cta);
+  if (sym_block > 0 && ct * 256 * VN >= symb_cend(row0 + r0, sym_block, ld)) return;  // whole tile above
+  for (int e = threadIdx.x; e < P * rows_per_cta; e += 256) {
+    const int i = e / rows_per_cta, r = e % rows_per_cta;
+    ksm[i][r] = (r0 + r < r1) ? K[(i64)i * pend_stride + (i64)gp * ld + row0 + r0 + r] : T(0);
+  }
+  __syncthreads();
+  if (col >= ld) return;
+  if (sym_block > 0 && col >= symb_cend(row0 + r0, sym_block, ld)) return;
+  Lanes<T, VN> wv[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const V t = *reinterpret_cast<const V*>(W + (i64)i * pend_stride + (i64)gp * ld + col);
+    memcpy(&wv[i], &t, sizeof(V));
+  }
+  T* C = cov + gp * stride_q + col;
+  for (i64 r = r0; r < r1; r += UNROLL) {
+    Lanes<T, VN> c[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j)
+      if (r + j < r1) {
+        const V t = ld_stream(reinterpret_cast<const V*>(C + (r + j) * ld));
+        memcpy(&c[j], &t, sizeof(V));
+      }
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j)
+      if (r + j < r1) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          const T kk = ksm[i][r + j - r0];
+#pragma unroll
+          for (int e = 0; e < VN; ++e) c[j].v[e] = sub_prod(c[j].v[e], kk, wv[i].v[e]);
+        }
+        V t;
+        memcpy(&t, &c[j], sizeof(V));
+        st_stream(reinterpret_cast<V*>(C + (r + j) * ld), t);
+      }
+  }
+}
+
+// k[c] <- (((k[c] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ...) with (a, b) = (x, c) for the entries the row
+// x keeps and (c, x) for the mirrored ones (lower-block storage): exactly what the deferred passes
+// will do to those entries.  grid (ceil(ld / 256), q).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict__ K, const T* __restrict__ W,
+                       i64 pend_stride, int p, const i64* __restrict__ idx_dev, i64 idx_host, i64 sym_block) {
+  const int gp = blockIdx.y;
+  const i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ld) return;
+  const i64 x = idx_dev ? *idx_dev : idx_host;
+  if (x < 0 || x >= N) return;
+  const bool mirrored = sym_block > 0 && c >= symb_cend(x, sym_block, ld);
+  T v = kbuf[(i64)gp * ld + c];
+  for (int i = 0; i < p; ++i) {
+    const T* Ki = K + (i64)i * pend_stride + (i64)gp * ld;
+    const T* Wi = W + (i64)i * pend_stride + (i64)gp * ld;
+    v = mirrored ? sub_prod(v, Ki[c], Wi[x]) : sub_prod(v, Ki[x], Wi[c]);
+  }
+  kbuf[(i64)gp * ld + c] = v;
+}
+
+template <typename T, int P>
+static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
+                        i64 pend_stride, i64 sym_block, cudaStream_t st) {
+  constexpr int VN = VecB<T>::n;
+  constexpr int UNROLL = P >= 16 ? 4 : 8;  // P w-vectors + UNROLL rows in registers: 2 CTAs per SM
+  const int rows_per_cta = 32;
+  const unsigned row_blocks = (unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta);
+  const unsigned col_tiles = (unsigned)((ld + 256 * VN - 1) / (256 * VN));
+  dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
+  rankb_kernel<T, P, UNROLL><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride,
+                                                   rows_per_cta, sym_block);
+  return 0;
+}
+
+template <typename T>
+static int rankb_dispatch(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
+                          i64 pend_stride, int p, i64 sym_block, cudaStream_t st) {
+  if (p <= 2) return launch_rankb<T, 2>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 4) return launch_rankb<T, 4>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 8) return launch_rankb<T, 8>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  return launch_rankb<T, 16>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+}
+
+}  // namespace tal
+
+using namespace tal;
+
+extern "C" {
+
+int tal_rankb_update(void* cov, long long cov_stride_q, long long ld, long long row0, long long n_loc,
+                     long long N, int q, const void* K, const void* W, long long pend_stride, int p,
+                     int lower, int dtype, void* stream) {
+  TAL_ARG(cov && K && W);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld == (N + 31) / 32 * 32 && n_loc >= 0);
+  TAL_ARG(p >= 1 && p <= TAL_MAX_PENDING && pend_stride >= (long long)q * ld);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(row0 % 32 == 0);
+  if (n_loc == 0) return TAL_OK;
+  const i64 blk = lower ? tal_sym_block(dtype) : 0;
+  const unsigned row_blocks = (unsigned)((n_loc + 31) / 32);
+  if (lower) TAL_ARG(row_blocks <= 65535);
+  if (dtype == TAL_F64)
+    rankb_dispatch<double>((double*)cov, cov_stride_q, ld, row0, n_loc, q, (const double*)K, (const double*)W,
+                           pend_stride, p, blk, as_stream(stream));
+  else
+    rankb_dispatch<float>((float*)cov, cov_stride_q, ld, row0, n_loc, q, (const float*)K, (const float*)W,
+                          pend_stride, p, blk, as_stream(stream));
+  TAL_LAUNCH_CHECK("tal_rankb_update");
+  return TAL_OK;
+}
+
+int tal_pending_correct_row(void* kbuf, long long ld, long long N, int q, const void* K, const void* W,
+                            long long pend_stride, int p, const long long* idx_dev, long long idx_host,
+                            int lower, int dtype, void* stream) {
+  TAL_ARG(kbuf && K && W && q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld >= N);
+  TAL_ARG(p >= 0 && p <= TAL_MAX_PENDING);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  if (p == 0) return TAL_OK;
+  const i64 blk = lower ? tal_sym_block(dtype) : 0;
+  dim3 grid((unsigned)((ld + 255) / 256), q);
+  if (dtype == TAL_F64)
+    pending_correct_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
+        (double*)kbuf, ld, N, (const double*)K, (const double*)W, pend_stride, p, idx_dev, idx_host, blk);
+  else
+    pending_correct_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
+        (float*)kbuf, ld, N, (const float*)K, (const float*)W, pend_stride, p, idx_dev, idx_host, blk);
+  TAL_LAUNCH_CHECK("tal_pending_correct_row");
+  return TAL_OK;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtal_b200.so")
 TAL_OK = 0
 TAL_MAX_Q = 16
 TAL_PEER_MAX = 16
+TAL_MAX_PENDING = 16
 TAL_PEER_HANDLE_BYTES = 64
 F64, F32 = 0, 1
 KERNEL_GAUSSIAN, KERNEL_LAPLACE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(5)
@@ -31,6 +32,31 @@ class ArgmaxResult(C.Structure):
         ("status", C.c_int),
         ("flags", C.c_int),
     ]
+
+
+TAL_CTX_REBASE = 6
+TAL_CTX_MAX_EVENTS = 64
+
+
+class StepCtx(C.Structure):
+    """tal_step_ctx of include/tal_b200.h (every field 8 bytes wide)."""
+    _fields_ = (
+        [("cov", C.c_void_p)] + [(n, C.c_longlong) for n in ("cov_stride_q", "ld", "row0", "n_loc", "N", "q", "dtype", "lower")]
+        + [(n, C.c_void_p) for n in ("mean", "var", "l", "u", "rho", "scal", "kbuf", "wbuf")]
+        + [("beta", C.c_double * 16)]
+        + [("Kp", C.c_void_p), ("Wp", C.c_void_p)]
+        + [(n, C.c_longlong) for n in ("pend_stride", "pend_slots", "update_block", "pending", "passes")]
+        + [("Wb", C.c_void_p)]
+        + [(n, C.c_longlong) for n in ("ldw", "cap_rows", "m_pad", "rows", "ncols", "cand0", "n_cand", "n_split", "cond_valid")]
+        + [(n, C.c_void_p) for n in ("cs", "app_scratch", "pcol")]
+        + [("F", C.c_void_p), ("safe", C.c_void_p), ("sample", C.c_void_p), ("first_constraint", C.c_longlong),
+           ("argmax_scratch", C.c_void_p), ("rec", C.c_void_p), ("combined", C.c_void_p)]
+        + [("y_table", C.c_void_p), ("y_stride", C.c_longlong)]
+        + [("mailboxes", C.c_void_p), ("mailbox", C.c_void_p), ("G", C.c_longlong), ("rank", C.c_longlong)]
+        + [("bounds", C.c_longlong * 17)]
+        + [("kbuf_off", C.c_longlong), ("pcol_off", C.c_longlong), ("pcol_peer", C.c_void_p), ("pcol_stride", C.c_longlong)]
+        + [("ev_start", C.c_void_p * 64), ("ev_stop", C.c_void_p * 64), ("n_ev", C.c_longlong), ("timing", C.c_longlong)]
+    )
 
 
 class TalError(RuntimeError):
@@ -104,12 +130,21 @@ SIGNATURES = {
                                _ll, _ll, _ll, _ll, _ll, _i, _p]),
     "tal_peer_wait_row": (_i, [_p, _i, _p, _ll, _p, _ll, _i, _p, _p]),
     "tal_sym_block": (_ll, [_i]),
+    "tal_rankb_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _ll, _i, _i, _i, _p]),
+    "tal_pending_correct_row": (_i, [_p, _ll, _ll, _i, _p, _p, _ll, _i, _p, _ll, _i, _i, _p]),
     "tal_rank1_update_lower": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _i, _p]),
     "tal_extract_row_lower": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _ll, _p, _p, _p, _i, _p]),
     "tal_gather_rows_lower": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _p, _ll, _i, _p]),
     "tal_rankm_update_lower": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p]),
     "tal_sym_mirror": (_i, [_p, _ll, _ll, _ll, _i, _i, _p]),
     "tal_peer_error": (_i, [_p, C.POINTER(_i), _p]),
+    "tal_step_ctx_bytes": (_ll, []),
+    "tal_ctx_select": (_i, [_p, _p]),
+    "tal_ctx_observe": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
+    "tal_ctx_step": (_i, [_p, _p]),
+    "tal_ctx_flush": (_i, [_p, _p]),
+    "tal_ctx_timing_begin": (_i, [_p]),
+    "tal_ctx_timing_read": (_i, [_p, C.POINTER(_d), C.POINTER(_ll), _p]),
     "tal_probe_fp64": (_i, [_i, _i, _i, _p, _p]),
 }
 

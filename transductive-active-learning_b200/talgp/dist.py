@@ -381,7 +381,7 @@ class ShardedITLBench:
         self.table_host = table
         self.table = torch.as_tensor(table, device=dev)
         self.inc = conditioning == "incremental"
-        self.ev = []
+        self.ev, self.pass_ms, self._tctx = [], [], None
         self._y_host = torch.zeros((1,), dtype=torch.float64).pin_memory()
         self._y_dev = torch.zeros((1,), dtype=torch.float64, device=dev)
 
@@ -418,22 +418,63 @@ class ShardedITLBench:
         return dict(zip(names, (acc / steps * 1e3).round(1).tolist()))  # microseconds
 
     def step(self, record: bool) -> None:
+        """One step, everything on the device.  With a live conditioning state the whole launch
+        sequence is one host call (tal_ctx_step); otherwise (first step, re-base) the Python sequence."""
+        gp = self.gp
+        st = gp._cond
+        if self.inc and gp._ctx_usable() and st is not None and st["valid"]:
+            gp.ctx_step(self.table, self.w["N"], self.beta, 1, None, None)
+            return
         rec = self._select()
         idx_dev = rec[0:1]
-        gp = self.gp
-        gp.exchange_row(idx_dev)
-        gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta)
-        if gp._cond is not None and gp._cond["valid"]:
-            gp._cond_downdate(idx_dev, 0)
-        if record:
+        if record and not (self.inc and gp._ctx_usable()):
+            gp.exchange_row(idx_dev)
+            gp.step_vectors(idx_dev, 0, self.table, self.w["N"], True, self.beta)
+            if gp._cond is not None and gp._cond["valid"]:
+                gp._cond_downdate(idx_dev, 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); gp.rank1_update(); e1.record()
+            e0.record(); passed = gp.rank1_update(); e1.record()
+            if passed:  # a pass over the matrix was launched (every update_block-th observation)
+                self.ev.append((e0, e1))
+        else:
+            gp.observe(idx_dev, self.table, self.beta, y_gather=True, y_stride=self.w["N"])
+
+    def timing_begin(self) -> None:
+        """CUDA events around every pass over the matrix from here on (C-side, csrc/stepctx.cu)."""
+        gp = self.gp
+        self.pass_ms, self.ev = [], []
+        self._tctx = gp._ctx_get() if (self.inc and gp._ctx_usable()) else None
+        if self._tctx is not None:
+            gp.lib.tal_ctx_timing_begin(C.byref(self._tctx))
+
+    def timing_end(self) -> None:
+        gp = self.gp
+        if self._tctx is not None:
+            from . import _abi
+            ms, n = (C.c_double * 64)(), C.c_longlong(0)
+            _abi.check(gp.lib.tal_ctx_timing_read(C.byref(self._tctx), ms, C.byref(n),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            self.pass_ms = [float(ms[i]) for i in range(int(n.value))]
+        else:
+            self.pass_ms = [a.elapsed_time(b) for a, b in self.ev]
+
+    def flush(self, record: bool = False) -> None:
+        """Apply the pending updates (end of a timed region: no work is left behind)."""
+        gp = self.gp
+        if getattr(self, "_tctx", None) is not None and gp._pending:
+            from . import _abi
+            self._tctx.pending = gp._pending
+            _abi.check(gp.lib.tal_ctx_flush(C.byref(self._tctx), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            gp._ctx_done(self._tctx)
+        elif record and gp._pending:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gp.flush(); e1.record()
             self.ev.append((e0, e1))
         else:
-            gp.rank1_update()
+            gp.flush()
 
     def rank1_ms(self) -> float:
-        return float(np.mean([a.elapsed_time(b) for a, b in self.ev])) if self.ev else 0.0
+        return float(np.mean(self.pass_ms)) if self.pass_ms else 0.0
 
     def e2e(self, steps: int) -> float:
         """The same steps with a host black box: every rank reads the combined
@@ -450,6 +491,7 @@ class ShardedITLBench:
             self._y_host[0] = float(self.table_host[0, r.idx])
             self._y_dev.copy_(self._y_host, non_blocking=True)
             self.gp.observe(rec[0:1], self._y_dev, self.beta)
+        self.gp.flush()
         t1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([t0.elapsed_time(t1)], device=self.gp.device, dtype=torch.float64)

@@ -106,7 +106,7 @@ class DeviceGP:
         self.ld = round_up(self.N, 32)
         self.rank1_variant = rank1_variant
         dev = self.device
-        self.cov = torch.zeros((q, self.n_loc, self.ld), dtype=dtype, device=dev)
+        self._cov = torch.zeros((q, self.n_loc, self.ld), dtype=dtype, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
         self.mean = torch.zeros((q, N), **f64)
         self.var = torch.zeros((q, N), **f64)
@@ -115,6 +115,12 @@ class DeviceGP:
         self.rho = torch.zeros((q, N), **f64)
         self.kbuf = torch.zeros((q, self.ld), dtype=dtype, device=dev)
         self.wbuf = torch.zeros((q, self.ld), dtype=dtype, device=dev)
+        # temporally blocked posterior update (csrc/rankb.cu): the (k, w) of up to `update_block`
+        # observations are kept pending and applied to the matrix in one pass
+        self.update_block = max(1, min(_abi.TAL_MAX_PENDING, int(os.environ.get("TAL_UPDATE_BLOCK", "16"))))
+        self._pending = 0
+        if self.update_block > 1:
+            self._alloc_pending()
         self.scal = torch.zeros((q,), **f64)
         self._argmax_scratch = torch.zeros((int(self.lib.tal_argmax_scratch_bytes()),),
                                            dtype=torch.uint8, device=dev)
@@ -141,6 +147,46 @@ class DeviceGP:
     def sharded(self) -> bool:
         return self.comm is not None
 
+    @property
+    def cov(self) -> torch.Tensor:
+        """[q, n_loc, ld] covariance rows with every pending update applied."""
+        self.flush()
+        return self._cov
+
+    def set_update_block(self, b: int) -> None:
+        """Number of observations whose covariance updates are applied in one pass (1 = a pass per
+        observation, like the reference)."""
+        self.flush()
+        self.update_block = max(1, min(_abi.TAL_MAX_PENDING, int(b)))
+        if self.update_block > 1:
+            self._alloc_pending()
+
+    def _alloc_pending(self) -> None:
+        """Pending (k, w) slots: the pass is compiled for 2, 4, 8 or 16 of them and reads that many
+        (the unused ones are zero)."""
+        slots = 2
+        while slots < self.update_block:
+            slots *= 2
+        self._Kp = torch.zeros((slots, self.q, self.ld), dtype=self.dtype, device=self.device)
+        self._Wp = torch.zeros((slots, self.q, self.ld), dtype=self.dtype, device=self.device)
+
+    def flush(self) -> bool:
+        """Apply the pending rank-1 updates to the matrix in one pass (bit-identical to applying
+        them one by one); returns whether a pass was launched."""
+        p = self._pending
+        if p == 0:
+            return False
+        _abi.check(self.lib.tal_rankb_update(
+            _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+            _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld, p, int(self.lower), self.dt, _stream()),
+            "tal_rankb_update")
+        self._Kp.zero_()
+        self._Wp.zero_()
+        self._pending = 0
+        if self.lower:
+            self._upper_stale = True
+        return True
+
     def _peer_attach(self, m_pad: int) -> None:
         """(Re)allocate the peer mailboxes; the observed-row buffer kbuf and the
         conditioning column then live inside this rank's mailbox, where the
@@ -156,11 +202,12 @@ class DeviceGP:
         if self._peer is None:
             self.extract_row(idx_dev, idx_host)
             self._sum(self.kbuf)
+            self.correct_row(idx_dev, idx_host)
             return
         st = self._cond if (self._cond is not None and self._cond["valid"]) else None
         pv, comm = self._peer, self.comm
         _abi.check(self.lib.tal_peer_push_row(
-            comm.table_ptr, comm.world, comm.rank, self._bounds_c, _ptr(self.cov), self.cov_stride_q,
+            comm.table_ptr, comm.world, comm.rank, self._bounds_c, _ptr(self._cov), self.cov_stride_q,
             self.ld, self.N, self.q, int(self.lower), _ptr(idx_dev), int(idx_host), pv.kbuf_off,
             _ptr(st["V"]) if st is not None else None,
             st["cap"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
@@ -168,6 +215,118 @@ class DeviceGP:
             "tal_peer_push_row")
         _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, comm.world, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
                                               self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
+        self.correct_row(idx_dev, idx_host)
+
+    # ------------------------------------------------- one step as one host call
+    def _ctx_usable(self) -> bool:
+        """The C-side step sequence (csrc/stepctx.cu) covers one GPU and the peer-memory sharded
+        model, with no conditioning state or the append form."""
+        if self.comm is not None and self._peer is None:
+            return False
+        st = self._cond
+        return st is None or st["append"]
+
+    def _ctx_get(self) -> "_abi.StepCtx":
+        st = self._cond
+        key = (None if st is None else st["V"].data_ptr(), None if st is None else st["cap"],
+               None if self._peer is None else self._peer.kbuf.data_ptr(), self.update_block,
+               self._Kp.data_ptr() if self.update_block > 1 else 0, self._cov.data_ptr())
+        c = getattr(self, "_ctx", None)
+        if c is None or self._ctx_key != key:
+            c = _abi.StepCtx()
+            c.cov, c.cov_stride_q, c.ld, c.row0, c.n_loc = self._cov.data_ptr(), self.cov_stride_q, self.ld, self.row0, self.n_loc
+            c.N, c.q, c.dtype, c.lower = self.N, self.q, self.dt, int(self.lower)
+            for name in ("mean", "var", "l", "u", "rho", "scal", "kbuf", "wbuf"):
+                setattr(c, name, getattr(self, name).data_ptr())
+            if self.update_block > 1:
+                c.Kp, c.Wp = self._Kp.data_ptr(), self._Wp.data_ptr()
+                c.pend_stride, c.pend_slots = self.q * self.ld, self._Kp.shape[0]
+            c.update_block = self.update_block
+            c.cand0, c.n_cand = self.cand0, self.n_cand
+            if st is not None:
+                c.Wb, c.ldw, c.cap_rows, c.m_pad, c.ncols = st["V"].data_ptr(), st["ncols"], st["cap"], st["m_pad"], st["ncols"]
+                c.n_split, c.cs, c.app_scratch, c.pcol = st["n_split"], st["cs"].data_ptr(), st["app"].data_ptr(), st["pcol"].data_ptr()
+            c.argmax_scratch = self._argmax_scratch.data_ptr()
+            c.rec, c.combined = self._result.data_ptr(), self._result.data_ptr()
+            c.G, c.rank = 1, 0
+            if self._peer is not None:
+                comm, pv = self.comm, self._peer
+                c.G, c.rank = comm.world, comm.rank
+                c.mailboxes, c.mailbox = comm._table.data_ptr(), comm._box
+                for g, b in enumerate(self.bounds):
+                    c.bounds[g] = b
+                for g in range(len(self.bounds), 17):
+                    c.bounds[g] = self.bounds[-1]
+                c.kbuf_off, c.pcol_off = pv.kbuf_off, pv.pcol_off
+                c.pcol_peer, c.pcol_stride = pv.pcol.data_ptr(), pv.pcol.shape[1]
+                c.combined = self._combined.data_ptr()
+            self._ctx, self._ctx_key = c, key
+        c.pending = self._pending
+        c.rows = st["rows"] if st is not None else 0
+        c.cond_valid = int(st is not None and st["valid"])
+        return c
+
+    def _ctx_done(self, c) -> None:
+        self._pending = int(c.pending)
+        if self._cond is not None:
+            self._cond["rows"] = int(c.rows)
+        if self.lower and c.passes:
+            self._upper_stale = True
+
+    def ctx_observe(self, idx_dev, idx_host, y_dev: torch.Tensor, y_stride: int, y_gather: bool,
+                    beta: Sequence[float]) -> None:
+        """`observe` through tal_ctx_observe: the whole per-observation launch sequence in one call."""
+        c = self._ctx_get()
+        for i in range(self.q):
+            c.beta[i] = float(beta[i])
+        rc = self.lib.tal_ctx_observe(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
+                                      int(bool(y_gather)), _stream())
+        if rc == _abi.TAL_CTX_REBASE:  # conditioning factor full: re-condition at the next scoring pass
+            self._cond["valid"] = False
+            c.cond_valid = 0
+            rc = self.lib.tal_ctx_observe(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
+                                          int(bool(y_gather)), _stream())
+        _abi.check(rc, "tal_ctx_observe")
+        self._ctx_done(c)
+
+    def ctx_step(self, y_table: torch.Tensor, y_stride: int, beta: Sequence[float], first_constraint: int,
+                 safe: Optional[torch.Tensor] = None, sample: Optional[torch.Tensor] = None) -> bool:
+        """One greedy step of directed ITL over the resident conditioning state in one host call
+        (score -> masked arg-max -> exchange -> update); returns whether a pass over the matrix was
+        launched.  The selection is left in `argmax_record()`."""
+        st = self._cond
+        if not (self._ctx_usable() and st is not None and st["valid"]):
+            raise _abi.TalError("ctx_step needs a valid resident conditioning state (score_itl_directed(incremental=True))")
+        c = self._ctx_get()
+        F = self._scratch("ctx_F", (max(self.n_cand, 1),))
+        c.F, c.safe, c.sample = F.data_ptr(), (safe.data_ptr() if safe is not None else None), (
+            sample.data_ptr() if sample is not None else None)
+        c.first_constraint = int(first_constraint)
+        c.y_table, c.y_stride = y_table.data_ptr(), int(y_stride)
+        for i in range(self.q):
+            c.beta[i] = float(beta[i])
+        passes = int(c.passes)
+        rc = self.lib.tal_ctx_step(C.byref(c), _stream())
+        if rc == _abi.TAL_CTX_REBASE:
+            st["valid"] = False
+            self._ctx_done(c)
+            return False
+        _abi.check(rc, "tal_ctx_step")
+        self._ctx_done(c)
+        return int(c.passes) > passes
+
+    def argmax_record(self) -> torch.Tensor:
+        return self._combined if self.comm is not None else self._result
+
+    def correct_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
+        """kbuf holds row idx of the matrix WITHOUT the pending updates: apply them to the row
+        (the same rounded operations the deferred pass will apply to those entries)."""
+        if self._pending == 0:
+            return
+        _abi.check(self.lib.tal_pending_correct_row(
+            _ptr(self.kbuf), self.ld, self.N, self.q, _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld,
+            self._pending, _ptr(idx_dev), int(idx_host), int(self.lower), self.dt, _stream()),
+            "tal_pending_correct_row")
 
     def _sum(self, buf: torch.Tensor) -> None:
         """Complete a buffer that only its owner filled (sum = broadcast)."""
@@ -204,22 +363,23 @@ class DeviceGP:
     def covariance_view(self, i: int) -> torch.Tensor:
         """[n_loc, N] view of GP i's covariance rows (no copy)."""
         self.ensure_full()
-        return self.cov[i, :, : self.N]
+        return self._cov[i, :, : self.N]
 
     def covariances_view(self) -> torch.Tensor:
         """[q, n_loc, N] view of all covariance rows (no copy)."""
         self.ensure_full()
-        return self.cov[:, :, : self.N]
+        return self._cov[:, :, : self.N]
 
     def ensure_full(self) -> None:
         """Lower-block storage: make the blocks above the diagonal valid again
         (mirror of the kept blocks) before a reader of full rows runs."""
+        self.flush()
         if not (self.lower and self._upper_stale):
             return
         if self.comm is not None:
             raise NotImplementedError("this operation reads full covariance rows; a row-sharded model in "
                                       "lower-block storage holds the mirror images on other ranks")
-        _abi.check(self.lib.tal_sym_mirror(_ptr(self.cov), self.cov_stride_q, self.ld, self.N, self.q,
+        _abi.check(self.lib.tal_sym_mirror(_ptr(self._cov), self.cov_stride_q, self.ld, self.N, self.q,
                                            self.dt, _stream()), "tal_sym_mirror")
         self._upper_stale = False
 
@@ -246,31 +406,33 @@ class DeviceGP:
         assert domain.dtype == torch.float64 and domain.is_contiguous()
         n, d = domain.shape
         assert n == self.N
+        self.flush()
         if self.q == 1:
             self._upper_stale = False  # (with several GPs the flag keeps covering the other ones)
         _abi.check(self.lib.tal_gram_stationary(
             kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
-            _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
+            _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
             "tal_gram_stationary")
         # diagonal of a stationary kernel: k(x, x), evaluated by the same kernel
         # on a one-row problem per point is wasteful; the diagonal entries of
         # the shard are copied instead and completed by the caller when sharded.
         if self.n_loc == self.N:
-            self.var[i].copy_(torch.diagonal(self.cov[i, :, : self.N]).to(torch.float64))
+            self.var[i].copy_(torch.diagonal(self._cov[i, :, : self.N]).to(torch.float64))
         else:
             sl = slice(self.row0, self.row0 + self.n_loc)
             self.var[i].zero_()
             self.var[i, sl].copy_(
-                torch.diagonal(self.cov[i, :, self.row0:self.row0 + self.n_loc]).to(torch.float64))
+                torch.diagonal(self._cov[i, :, self.row0:self.row0 + self.n_loc]).to(torch.float64))
             self._sum(self.var[i])  # every shard contributed its own diagonal block
 
     def load_covariance(self, i: int, cov) -> None:
         """Upload a full N x N covariance (host or device) into shard i."""
         src = torch.as_tensor(cov)
+        self.flush()
         if self.q == 1:
             self._upper_stale = False  # (with several GPs the flag keeps covering the other ones)
         rows = src[self.row0:self.row0 + self.n_loc]
-        self.cov[i, :, : self.N].copy_(rows.to(device=self.device, dtype=self.dtype))
+        self._cov[i, :, : self.N].copy_(rows.to(device=self.device, dtype=self.dtype))
         self.var[i].copy_(torch.diagonal(src).to(device=self.device, dtype=torch.float64))
         if self.dtype != torch.float64:  # keep var == diag(cov) in the storage precision
             self.var[i].copy_(self.var[i].to(self.dtype).to(torch.float64))
@@ -286,7 +448,7 @@ class DeviceGP:
     def extract_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
         fn = self.lib.tal_extract_row_lower if self.lower else self.lib.tal_extract_row
         _abi.check(fn(
-            _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+            _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(idx_dev), int(idx_host), _ptr(self.mean), _ptr(self.kbuf), _ptr(self.scal),
             self.dt, _stream()), "tal_extract_row")
 
@@ -299,15 +461,28 @@ class DeviceGP:
             _ptr(self.mean), _ptr(self.var), _ptr(self.l), _ptr(self.u), self.dt, _stream()),
             "tal_step_vectors")
 
-    def rank1_update(self, variant: Optional[int] = None) -> None:
+    def rank1_update(self, variant: Optional[int] = None) -> bool:
+        """The covariance update of the current observation (kbuf, wbuf).  With
+        update_block > 1 it is queued and applied together with the next ones
+        (`flush`); returns whether a pass over the matrix was launched."""
+        if self.update_block > 1 and variant is None:
+            self._Kp[self._pending].copy_(self.kbuf)
+            self._Wp[self._pending].copy_(self.wbuf)
+            self._pending += 1
+            return self.flush() if self._pending >= self.update_block else False
+        self.flush()
+        self._rank1_now(variant)
+        return True
+
+    def _rank1_now(self, variant: Optional[int] = None) -> None:
         if self.lower:
             self._upper_stale = True
             _abi.check(self.lib.tal_rank1_update_lower(
-                _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+                _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
                 _ptr(self.kbuf), _ptr(self.wbuf), self.dt, _stream()), "tal_rank1_update_lower")
             return
         _abi.check(self.lib.tal_rank1_update(
-            _ptr(self.cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
+            _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(self.kbuf), _ptr(self.wbuf), self.dt,
             self.rank1_variant if variant is None else variant, _stream()), "tal_rank1_update")
 
@@ -333,9 +508,13 @@ class DeviceGP:
             if self._y_event is None:
                 self._y_event = torch.cuda.Event()
             self._y_event.record()
+        if allreduce is None and self._ctx_usable():
+            self.ctx_observe(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
+            return
         if allreduce is not None:
             self.extract_row(idx_dev, idx_host)
             allreduce(self.kbuf)
+            self.correct_row(idx_dev, idx_host)
         else:
             self.exchange_row(idx_dev, idx_host)
         self.step_vectors(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
@@ -352,6 +531,7 @@ class DeviceGP:
         m_total = int(obs_idx.numel())
         if m_total == 0:  # :23-24 short-circuit
             return
+        self.flush()
         if self._cond is not None:
             self._cond["valid"] = False  # general-m update: re-condition from scratch next time
         obs_idx = obs_idx.to(device=self.device, dtype=torch.int64).contiguous()
@@ -368,7 +548,7 @@ class DeviceGP:
             oi = obs_idx[s:e]
             gather = self.lib.tal_gather_rows_lower if self.lower else self.lib.tal_gather_rows
             _abi.check(gather(
-                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(oi), m, _ptr(B),
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(oi), m, _ptr(B),
                 ldb, self.dt, _stream()), "tal_gather_rows")
             if allreduce is not None:
                 allreduce(B)
@@ -381,7 +561,7 @@ class DeviceGP:
                 "tal_small_posterior_weights")
             update = self.lib.tal_rankm_update_lower if self.lower else self.lib.tal_rankm_update
             _abi.check(update(
-                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(B), _ptr(W), ldb,
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(B), _ptr(W), ldb,
                 m, self.dt, _stream()), "tal_rankm_update")
             if self.lower:
                 self._upper_stale = True
@@ -432,6 +612,7 @@ class DeviceGP:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
         lib = self.lib
         N = self.N
+        self.flush()
         if self.lower:
             return self._score_rows_lower(rule, roi_idx, m, p0, p1)
         sharded_cols = sharded_cols or self.sharded
@@ -462,12 +643,12 @@ class DeviceGP:
             pp0 = float(p0[i]) if p0 is not None else 0.0
             if sharded_cols:
                 _abi.check(lib.tal_colsum_cols(
-                    rule, _ptr(self.cov[i]), self.ld, self.n_loc, _ptr(roi_idx), m, _ptr(w),
+                    rule, _ptr(self._cov[i]), self.ld, self.n_loc, _ptr(roi_idx), m, _ptr(w),
                     _ptr(dinv[off:]) if dinv is not None else None, pp0, float(p1), _ptr(c),
                     self.dt, _stream()), "tal_colsum_cols")
             else:
                 _abi.check(lib.tal_colsum_rows(
-                    rule, _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m,
+                    rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m,
                     _ptr(w), _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt,
                     _stream()), "tal_colsum_rows")
             if rule == _abi.RULE_VTL:
@@ -509,7 +690,7 @@ class DeviceGP:
                                                 _ptr(dinv), _stream()), "tal_pred_var_inv")
             pp0 = float(p0[i]) if p0 is not None else 0.0
             _abi.check(lib.tal_colsum_lower(
-                rule, _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(w),
+                rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(w),
                 _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt, _stream()),
                 "tal_colsum_lower")
             self._sum(c)
@@ -534,6 +715,7 @@ class DeviceGP:
         and cs.  Row-sharded: cov[A, x] is read as the symmetric cov[x, A], Sigma_AA
         is assembled from the owners' rows by a sum, its Cholesky is replicated."""
         lib = self.lib
+        self.flush()
         m_pad, ncols = self._cond_dims(m)
         ldb = ncols
         S = self._scratch("cv_S", (m_pad, m_pad))
@@ -543,12 +725,12 @@ class DeviceGP:
             self._gather_roi_lower_sharded(i, roi_idx, m, m_pad, ncols, jitter, S, B)
         elif self.comm is None:
             gather = lib.tal_gather_roi_lower if self.lower else lib.tal_gather_roi
-            _abi.check(gather(_ptr(self.cov[i]), self.ld, self.N, _ptr(roi_idx), m,
+            _abi.check(gather(_ptr(self._cov[i]), self.ld, self.N, _ptr(roi_idx), m,
                                           m_pad, float(jitter), _ptr(S), m_pad, _ptr(B), ldb,
                                           self.dt, _stream()), "tal_gather_roi")
         else:
             _abi.check(lib.tal_gather_roi_sharded(
-                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, _ptr(roi_idx), m, m_pad,
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, _ptr(roi_idx), m, m_pad,
                 float(jitter), _ptr(S), m_pad, _ptr(B), ldb, ncols, self.dt, _stream()),
                 "tal_gather_roi_sharded")
             self._sum(S)
@@ -575,7 +757,7 @@ class DeviceGP:
         for j0 in range(0, m, 64):
             j1 = min(m, j0 + 64)
             _abi.check(self.lib.tal_gather_rows_lower(
-                _ptr(self.cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(idx[j0:j1]), j1 - j0,
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(idx[j0:j1]), j1 - j0,
                 _ptr(rows), self.ld, self.dt, _stream()), "tal_gather_rows_lower")
             self._sum(rows)
             B[j0:j1, : self.n_cand] = rows[: j1 - j0, self.cand0: self.cand0 + self.n_cand]
