@@ -382,6 +382,7 @@ def run_ours(args, w):
         clocks.start()  # sampled from the warm-up on: the timed region alone can be shorter than one sample
         for _ in range(args.warmup):
             dev_step(False)
+        gp.flush()  # the timed region starts and ends with no update pending: exactly K steps of work
         torch.cuda.synchronize()
         l_start, u_start = gp.l.clone(), gp.u.clone()
         lib.tal_reset_launch_count()
@@ -569,6 +570,7 @@ def run_ours(args, w):
     warm_run = max(args.warmup, 200)
     for _ in range(warm_run):
         bench.step(False)
+    bench.flush()  # the timed region starts and ends with no update pending: exactly K steps of work
     torch.cuda.synchronize()
     dist.barrier()
     lib.tal_reset_launch_count()
