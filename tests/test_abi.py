@@ -58,3 +58,11 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def test_step_ctx_layout_matches_header(lib_path):
+    """The ctypes mirror of tal_step_ctx has the size the library was compiled with."""
+    import ctypes
+    from talgp import _abi
+    lib = _abi.load()
+    assert lib.tal_step_ctx_bytes() == ctypes.sizeof(_abi.StepCtx)
