@@ -1,6 +1,13 @@
 import os
 import sys
 
+# The single-GPU emulation of the peer-memory protocol (tests/test_gpu_sharded.py, exchange="peer") runs
+# shards whose kernels WAIT ON EACH OTHER inside one CUDA context.  With lazy module loading the first
+# launch of a kernel in one thread loads its module under a context-wide lock while the other thread's
+# kernel spins, which stalls until that kernel's time-out; load everything up front instead.  (Between
+# processes on separate GPUs — the real deployment — nothing is shared and this cannot occur.)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -200,9 +200,10 @@ class DeviceGP:
         scal <- mean[:, idx]; in peer mode also pcol <- V[:, :, idx] when the
         incremental conditioning is live."""
         if self._peer is None:
-            self.extract_row(idx_dev, idx_host)
-            self._sum(self.kbuf)
-            self.correct_row(idx_dev, idx_host)
+            self.extract_row(idx_dev, idx_host)  # (one GPU: corrected for the pending updates there)
+            if self.comm is not None:
+                self._sum(self.kbuf)
+                self.correct_row(idx_dev, idx_host)
             return
         st = self._cond if (self._cond is not None and self._cond["valid"]) else None
         pv, comm = self._peer, self.comm
@@ -445,12 +446,17 @@ class DeviceGP:
         self.u.copy_(self.mean + b * sd)
 
     # ------------------------------------------------------------------ update
-    def extract_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0) -> None:
+    def extract_row(self, idx_dev: Optional[torch.Tensor], idx_host: int = 0, correct: bool = True) -> None:
+        """kbuf <- this shard's part of row idx (zeros elsewhere) and scal <- mean[:, idx].  On one GPU
+        the pending updates are applied to the row as well (`correct`); a sharded caller does that
+        after the sum over the shards (`exchange_row`)."""
         fn = self.lib.tal_extract_row_lower if self.lower else self.lib.tal_extract_row
         _abi.check(fn(
             _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(idx_dev), int(idx_host), _ptr(self.mean), _ptr(self.kbuf), _ptr(self.scal),
             self.dt, _stream()), "tal_extract_row")
+        if correct and self.comm is None:
+            self.correct_row(idx_dev, idx_host)
 
     def step_vectors(self, idx_dev: Optional[torch.Tensor], idx_host: int, y_dev: torch.Tensor,
                      y_stride: int, y_gather: bool, beta: Sequence[float]) -> None:
@@ -512,7 +518,7 @@ class DeviceGP:
             self.ctx_observe(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
             return
         if allreduce is not None:
-            self.extract_row(idx_dev, idx_host)
+            self.extract_row(idx_dev, idx_host, correct=False)
             allreduce(self.kbuf)
             self.correct_row(idx_dev, idx_host)
         else:
