@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TAL_ABI_VERSION 2
+#define TAL_ABI_VERSION 3
 #define TAL_MAX_Q 16
 
 /* status codes */
@@ -46,10 +46,19 @@ extern "C" {
 #define TAL_ARGMAX_EMPTY_SAFE_SET 2 /* "Operating safe set is empty. Cannot make observations." */
 #define TAL_ARGMAX_ALL_NEG_INF 3    /* "Objective is negative infinity everywhere." */
 #define TAL_ARGMAX_ALL_NAN 4        /* "Objective is NaN everywhere." */
+#define TAL_ARGMAX_PEER_ERROR 7     /* row-sharded model: an NVLink peer exchange timed out (flags bit 3) */
 
 /* dtype */
 #define TAL_F64 0
 #define TAL_F32 1
+/* arithmetic of the covariance update c <- c - k*w, OR-ed into the `dtype` argument of
+ * tal_step_vectors, tal_rank1_update[_lower], tal_rankb_update, tal_pending_correct_row and
+ * the step context: without it the product is rounded before the subtraction (two roundings,
+ * what NumPy and an unfused XLA dot + subtract compute: lib/gp/gaussian_distribution.py:36);
+ * with it the update is one fused multiply-subtract (one rounding, what a fused XLA:CPU loop
+ * compiled with FMA contraction computes).  The matrix, the pending rows and the variance
+ * vector always use the same mode, so var == diag(cov) holds bit for bit in either. */
+#define TAL_ARITH_FMA 16
 
 /* stationary kernel kinds — lib/gp/kernels/stationary.py:23-55 */
 #define TAL_KERNEL_GAUSSIAN 0
@@ -70,7 +79,8 @@ typedef struct tal_argmax_result {
   double val;       /* nanmax of the safety-masked objective */
   long long n_ties; /* number of points attaining val exactly */
   int status;       /* TAL_ARGMAX_* (derived from flags) */
-  int flags;        /* bit0: safe set non-empty; bit1: some F != -inf; bit2: some safe F not NaN */
+  int flags;        /* bit0: safe set non-empty; bit1: some F != -inf; bit2: some safe F not NaN;
+                       bit3: a peer exchange of this rank timed out (TAL_ARGMAX_PEER_ERROR) */
 } tal_argmax_result;
 
 /* ---- library --------------------------------------------------------- */
@@ -427,13 +437,15 @@ int tal_peer_combine_records(void* mailbox, int G, tal_argmax_result* out, void*
  * column idx.  If V != null (V is [q][m_pad][ldv] fp64, the incremental-
  * conditioning state of candidates [cand0, cand0 + n_cand)) the rank whose
  * candidate range contains idx also stores the column V[:, :, idx - cand0] into
- * every mailbox's pcol.  tal_peer_wait_row blocks the stream until the G pieces of this
+ * every mailbox's pcol (GP i's column at pcol + i * pcol_stride doubles; pcol_stride >= m_pad
+ * is the row length of the mailbox's pcol area, m_pad the number of rows in use).  tal_peer_wait_row blocks the stream until the G pieces of this
  * exchange have landed and writes scal[i] = mean[i][idx].                       */
 int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* bounds_host, const void* cov,
                       long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
-                      long long pcol_off, long long cand0, long long n_cand, int dtype, void* stream);
+                      long long pcol_off, long long pcol_stride, long long cand0, long long n_cand, int dtype,
+                      void* stream);
 int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,
                       long long N, int q, double* scal, void* stream);
 int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synchronises */
@@ -442,23 +454,36 @@ int tal_peer_error(const void* mailbox, int* error_host, void* stream); /* synch
  * The per-step launch sequence of the greedy loop (lib/algorithms/__init__.py:77-94
  * with the directed-ITL rule over a resident conditioning state) issued from a
  * context that the host fills once: every field is 8 bytes wide (pointers, long
- * long, double), device pointers unless noted.  The functions only call the entry
- * points above; the counters `pending`, `rows`, `passes`, `n_ev` are advanced here
- * and read back by the host.
- *   tal_ctx_select   F = directed-ITL score of this rank's candidates from (var, cs, rho);
- *                    masked arg-max into `combined` (sharded: into `rec`, then the peer
- *                    all-gather + combine).
- *   tal_ctx_observe  row idx into kbuf (extract, or the peer exchange incl. the
- *                    conditioning column), pending-row correction, step vectors, the
- *                    append-form conditioning update of every GP (if cond_valid), then
- *                    the covariance update: queued, and applied to the matrix in one
- *                    pass every `update_block` observations (update_block = 1: at once).
- *                    Returns TAL_CTX_REBASE (nothing enqueued) when the conditioning
- *                    factor is full: the host re-conditions from scratch.
+ * long, double), device pointers unless noted.  The O(N) work of a step is fused
+ * into three kernels (csrc/fused.cu: observed row + pending correction + step
+ * vectors; the read-only pass over the conditioning factor incl. the column
+ * gather; appended rows + cs + score + masked arg-max [+ peer publish]); they
+ * compute every value with the same sequence of rounded operations as the
+ * stand-alone entry points above.  The counters `pending`, `rows`, `passes`,
+ * `n_ev`, `sel_state`, `scal_ok` are advanced here and read back by the host.
+ *   tal_ctx_select   makes `combined` hold the selection for the current state:
+ *                    nothing to launch when the previous tal_ctx_observe already
+ *                    produced it (auto_select), otherwise F = directed-ITL score of
+ *                    this rank's candidates from (var, cs, rho) and the masked
+ *                    arg-max (sharded: peer all-gather + combine).
+ *   tal_ctx_observe  row idx (own rows, or the peer exchange incl. the conditioning
+ *                    column; the arg-max records published by the previous step are
+ *                    combined inside the same kernel), pending-row correction, step
+ *                    vectors, the append-form conditioning update of every GP (if
+ *                    cond_valid) and, with auto_select != 0, the selection of the
+ *                    next candidate; then the covariance update: queued, and applied
+ *                    to the matrix in one pass every `update_block` observations
+ *                    (update_block = 1: at once).  y_dev == null: the observation
+ *                    value is not known yet: everything that does not depend on it
+ *                    is applied and tal_ctx_observe_y completes mean, l, u later.
+ *                    Returns TAL_CTX_REBASE after enqueueing the observation WITHOUT
+ *                    the conditioning update when the factor is full: the caller
+ *                    re-conditions from scratch before the next score.
  *   tal_ctx_step     select + observe with y taken from y_table[i][idx].
  *   tal_ctx_flush    applies the pending updates now.
  *   tal_ctx_timing_begin / _read: CUDA events around every pass over the matrix
- *                    (read synchronises the stream): the kernel times bench.py reports. */
+ *                    (read synchronises the stream; updates_out[i] = number of
+ *                    rank-1 updates that pass applied): the kernel times bench.py reports. */
 #define TAL_CTX_REBASE 6
 #define TAL_CTX_MAX_EVENTS 64
 typedef struct tal_step_ctx {
@@ -483,15 +508,27 @@ typedef struct tal_step_ctx {
   long long kbuf_off, pcol_off; const double* pcol_peer; long long pcol_stride;
   /* pass timing (host handles) */
   void* ev_start[TAL_CTX_MAX_EVENTS]; void* ev_stop[TAL_CTX_MAX_EVENTS]; long long n_ev, timing;
+  long long ev_updates[TAL_CTX_MAX_EVENTS];
+  /* fused step */
+  long long arith;                   /* != 0: one-rounding update arithmetic (TAL_ARITH_FMA) */
+  long long auto_select;             /* != 0: tal_ctx_observe also selects the next candidate */
+  long long sel_state;               /* 0 none, 1 record published to the peers, 2 `combined` is current */
+  long long scal_ok;                 /* scal holds mean[:, combined.idx] */
+  const unsigned char *sel_safe, *sel_sample; long long sel_fc;  /* masks the selection was made under */
+  void* fz_scratch;                  /* tal_fused_scratch_bytes(q, ncols, n_split) */
 } tal_step_ctx;
 long long tal_step_ctx_bytes(void);
+long long tal_fused_scratch_bytes(int q, long long ncols, int n_split);
 int tal_ctx_select(tal_step_ctx* ctx, void* stream);
 int tal_ctx_observe(tal_step_ctx* ctx, const long long* idx_dev, long long idx_host, const double* y_dev,
                     long long y_stride, int y_gather, void* stream);
+int tal_ctx_observe_y(tal_step_ctx* ctx, const long long* idx_dev, long long idx_host, const double* y_dev,
+                      long long y_stride, int y_gather, void* stream);
 int tal_ctx_step(tal_step_ctx* ctx, void* stream);
 int tal_ctx_flush(tal_step_ctx* ctx, void* stream);
 int tal_ctx_timing_begin(tal_step_ctx* ctx);
-int tal_ctx_timing_read(tal_step_ctx* ctx, double* ms_out_host, long long* n_out_host, void* stream);
+int tal_ctx_timing_read(tal_step_ctx* ctx, double* ms_out_host, long long* updates_out_host,
+                        long long* n_out_host, void* stream);
 
 /* ---- fp64 peak probes (roofline denominators of the tensor path) --------
  * kind 0: DMMA.8x8x4, kind 1: DFMA; `blocks` CTAs x 256 threads x iters x 16

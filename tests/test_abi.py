@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     missing = [n for n in _declared() if not hasattr(lib, n)]
     assert not missing, missing
     lib.tal_abi_version.restype = ctypes.c_int
-    assert lib.tal_abi_version() == 2
+    assert lib.tal_abi_version() == 3
 
 
 def test_binding_covers_every_declared_symbol(lib_path):

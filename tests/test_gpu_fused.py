@@ -1,0 +1,248 @@
+"""The fused step (csrc/fused.cu + stepctx.cu: 3 kernels per step, 4 when sharded) against the
+kernel-by-kernel sequence it replaces (extract row -> pending correction -> step vectors -> column
+extract -> append-form conditioning -> score -> masked arg-max): every rounded operation is the
+same, so the model state is BIT-IDENTICAL; the conditioning sums are split differently (per-split
+partial sums), so scores agree to rounding.  Both update arithmetics, both storage modes, q = 1, 2;
+failed arg-max; factor capacity reached; row-sharded over the peer-memory exchange."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(cuda, N, q, storage, arith, fused, dtype=torch.float64, block=16, comm=None, seed=3):
+    from talgp import _abi
+    from talgp.engine import DeviceGP
+    rng = np.random.default_rng(seed)
+    dom = torch.as_tensor(rng.random((N, 3)), device=cuda)
+    gp = DeviceGP(N, q, dtype=dtype, device=cuda, storage=storage, arith=arith, comm=comm)
+    gp.fused = fused
+    gp.set_update_block(block)
+    for i in range(q):
+        gp.build_gram(i, _abi.KERNEL_MATERN52 if i % 2 == 0 else _abi.KERNEL_GAUSSIAN, 1.0 + 0.5 * i, 0.3 + 0.1 * i, dom)
+    gp.rho.fill_(0.1)
+    gp.init_bounds([2.0] * q)
+    return gp
+
+
+def _kept(gp, cuda):
+    blk = int(gp.lib.tal_sym_block(gp.dt))
+    r = torch.arange(gp.row0, gp.row0 + gp.n_loc, device=cuda)
+    return torch.arange(gp.ld, device=cuda)[None, :] < torch.clamp((r // blk + 1) * blk, max=gp.ld)[:, None]
+
+
+def _same_state(a, b, cuda):
+    for name in ("mean", "var", "l", "u"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    if a.lower:
+        k = _kept(a, cuda)
+        assert torch.equal(a.cov[:, k], b.cov[:, k])
+    else:
+        assert torch.equal(a.cov, b.cov)
+
+
+@pytest.mark.parametrize("arith", ["two_rounding", "fma"])
+@pytest.mark.parametrize("storage", ["full", "lower"])
+@pytest.mark.parametrize("q,dtype", [(1, torch.float64), (2, torch.float64), (2, torch.float32)])
+def test_fused_step_matches_unfused_sequence(cuda, q, dtype, storage, arith):
+    N, m, T = 1700, 130, 40
+    rng = np.random.default_rng(5)
+    roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
+    table = torch.as_tensor(rng.standard_normal((q, N)), device=cuda)
+    sample = torch.ones((N,), dtype=torch.uint8, device=cuda)
+    sample[::7] = 0
+    ref = _make(cuda, N, q, storage, arith, fused=False, dtype=dtype)
+    gp = _make(cuda, N, q, storage, arith, fused=True, dtype=dtype)
+    fc = 1
+    tol = dict(rtol=1e-9, atol=1e-12) if dtype == torch.float64 else dict(rtol=1e-4, atol=1e-7)
+    for t in range(T):
+        # reference: kernel by kernel
+        Fr = ref.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+        rr = ref.read_result(ref.masked_argmax(Fr, None, fc, sample))
+        ref.observe(ref._result[0:1].clone(), table, [2.0] * q, y_gather=True, y_stride=N)
+        # fused: the first step conditions from scratch, then one host call per step
+        st = gp._cond
+        if st is None or not st["valid"]:
+            F = gp.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+            rec = gp.masked_argmax(F, None, fc, sample)
+            rf = gp.read_result(rec)
+            gp.observe(rec[0:1].clone(), table, [2.0] * q, y_gather=True, y_stride=N)
+        else:
+            gp.ctx_step(table, N, [2.0] * q, fc, None, sample)
+            rf = gp.read_result(gp.argmax_record())
+            F = gp._scratch("ctx_F", (N,))
+            fin = torch.isfinite(Fr)
+            torch.testing.assert_close(F[fin], Fr[fin], **tol)
+            assert torch.equal(torch.isneginf(F), torch.isneginf(Fr))
+        assert rf.status == 0 and rr.status == 0
+        assert rf.idx == rr.idx or abs(rf.val - rr.val) <= 1e-9 * max(1.0, abs(rr.val)), (t, rf.idx, rr.idx)
+        if rf.idx != rr.idx:
+            pytest.skip("near-tie resolved differently by the two summation orders")
+        assert torch.equal(gp.kbuf, ref.kbuf) and torch.equal(gp.wbuf, ref.wbuf), t
+    _same_state(gp, ref, cuda)
+    for i in range(q):
+        assert torch.equal(torch.diagonal(gp.cov[i, :, :N]).to(torch.float64), gp.var[i])
+    torch.testing.assert_close(gp._cond["cs"], ref._cond["cs"], **tol)
+    assert gp._cond["rows"] == ref._cond["rows"]
+
+
+def test_fused_observe_api_and_host_values(cuda):
+    """`observe` with a host index / host observation (the drop-in API's path) goes through the same
+    fused kernels; y supplied later (tal_ctx_observe_y) gives the same state as y supplied at once."""
+    N, q = 900, 2
+    a = _make(cuda, N, q, "lower", "two_rounding", fused=True)
+    b = _make(cuda, N, q, "lower", "two_rounding", fused=False)
+    c = _make(cuda, N, q, "lower", "two_rounding", fused=True)
+    rng = np.random.default_rng(2)
+    ydev = torch.zeros((q,), dtype=torch.float64, device=cuda)
+    for t in range(21):
+        idx = int(rng.integers(N))
+        y = rng.standard_normal(q)
+        a.observe(idx, y, [2.0] * q)
+        b.observe(idx, y, [2.0] * q)
+        ydev.copy_(torch.as_tensor(y))
+        c.ctx_observe(None, idx, None, 1, False, [2.0] * q)        # everything that does not need y
+        c.ctx_observe_y(None, idx, ydev, 1, False)                 # mean, l, u
+        c._ctx_done(c._ctx)
+    _same_state(a, b, cuda)
+    _same_state(c, b, cuda)
+
+
+def test_failed_argmax_is_a_noop_on_the_device(cuda):
+    """An empty safe set gives idx = -1: the step that follows changes nothing."""
+    N, m = 800, 60
+    gp = _make(cuda, N, 2, "lower", "two_rounding", fused=True)
+    roi = torch.arange(0, m * 3, 3, device=cuda)
+    table = torch.zeros((2, N), dtype=torch.float64, device=cuda)
+    F = gp.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+    rec = gp.masked_argmax(F, None, 1, None)
+    gp.observe(rec[0:1].clone(), table, [2.0, 2.0], y_gather=True, y_stride=N)
+    gp.flush()
+    before = {n: getattr(gp, n).clone() for n in ("mean", "var", "l", "u")}
+    cov0, cs0 = gp.cov.clone(), gp._cond["cs"].clone()
+    gp.l[1].fill_(-1.0)  # constraint GP pessimistically unsafe everywhere
+    before["l"] = gp.l.clone()
+    gp.ctx_step(table, N, [2.0, 2.0], 1, None, None)  # selects under the new bounds: empty safe set
+    gp.ctx_step(table, N, [2.0, 2.0], 1, None, None)  # observes idx = -1
+    gp.flush()
+    res = gp.read_result(gp.argmax_record())
+    assert res.status == 2 and res.idx == -1
+    for n in before:
+        assert torch.equal(getattr(gp, n), before[n]), n
+    assert torch.equal(gp.cov, cov0) and torch.equal(gp._cond["cs"], cs0)
+    assert bool(torch.isfinite(gp._cond["V"]).all())
+
+
+def test_capacity_reached_applies_the_observation_and_rebases(cuda, monkeypatch):
+    """When the conditioning factor is full the step is still carried out (it used to be
+    dropped) and the next scoring pass re-conditions from scratch."""
+    monkeypatch.setenv("TAL_COND_CAPACITY", "5")
+    N, m, T = 1100, 100, 17
+    rng = np.random.default_rng(9)
+    roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
+    table = torch.as_tensor(rng.standard_normal((1, N)), device=cuda)
+    gp = _make(cuda, N, 1, "lower", "fma", fused=True)
+    ref = _make(cuda, N, 1, "lower", "fma", fused=False)
+    assert gp.cond_capacity == 5
+    n_obs = 0
+    for t in range(T):
+        Fr = ref.score_itl_directed(roi, m, incremental=False)
+        ref.masked_argmax(Fr, None, 1, None)
+        ri = int(ref._result[0].item())
+        st = gp._cond
+        if st is None or not st["valid"]:
+            F = gp.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+            rec = gp.masked_argmax(F, None, 1, None)
+            gi = int(rec[0].item())
+            gp.observe(rec[0:1].clone(), table, [2.0], y_gather=True, y_stride=N)
+        else:
+            gp.ctx_step(table, N, [2.0], 1, None, None)
+            gi = int(gp.argmax_record()[0].item())
+        n_obs += 1
+        assert gi == ri or abs(float(Fr[gi]) - float(Fr[ri])) <= 1e-7 * max(1.0, abs(float(Fr[ri]))), t
+        ref.observe(gi, table[:, gi].cpu().numpy(), [2.0])  # teacher-forced with the fused selection
+    gp.flush(); ref.flush()
+    torch.testing.assert_close(gp.var, ref.var, rtol=1e-12, atol=0)
+    torch.testing.assert_close(gp.mean, ref.mean, rtol=1e-10, atol=1e-13)
+    assert n_obs == T
+
+
+def _threads(G, fn):
+    errs = []
+    shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
+
+    def worker(rank):
+        try:
+            fn(rank, shared)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            shared["barrier"].abort()
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+
+
+@pytest.mark.parametrize("storage", ["full", "lower"])
+@pytest.mark.parametrize("q", [1, 2])
+@pytest.mark.parametrize("G", [2, 3])
+def test_fused_step_row_sharded_peer(cuda, G, q, storage):
+    """tal_ctx_step on every shard over the peer-memory exchange (records published by the last block of
+    fused_finish, combined inside the push kernel; one stream per shard on ONE GPU) reproduces the
+    single-GPU fused run; q = 2 covers the per-GP stride of the exchanged conditioning column."""
+    from talgp.dist import LocalPeerComm
+    N, m, T = 2500, 140, 22
+    rng = np.random.default_rng(6)
+    roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
+    table = torch.as_tensor(rng.standard_normal((q, N)), device=cuda)
+    one = _make(cuda, N, q, storage, "fma", fused=True)
+    sel1 = []
+    for t in range(T):
+        st = one._cond
+        if st is None or not st["valid"]:
+            F = one.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+            rec = one.masked_argmax(F, None, 1, None)
+            one.observe(rec[0:1].clone(), table, [2.0] * q, y_gather=True, y_stride=N)
+        else:
+            one.ctx_step(table, N, [2.0] * q, 1, None, None)
+        sel1.append(int(one.argmax_record()[0].item()))
+    one.flush()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    out = [None] * G
+
+    def body(rank, shared):
+        torch.cuda.set_device(cuda)
+        with torch.cuda.stream(torch.cuda.Stream(device=cuda)):
+            comm = LocalPeerComm(shared, rank, G)
+            gp = _make(cuda, N, q, storage, "fma", fused=True, comm=comm)
+            sel = []
+            for t in range(T):
+                st = gp._cond
+                if st is None or not st["valid"]:
+                    F = gp.score_itl_directed(roi, m, incremental=True, roi_key=roi)
+                    rec = gp.argmax_candidates(F, None, 1, None)
+                    gp.observe(rec[0:1], table, [2.0] * q, y_gather=True, y_stride=N)
+                else:
+                    gp.ctx_step(table, N, [2.0] * q, 1, None, None)
+                sel.append(int(gp.argmax_record()[0].item()))
+            gp.flush()
+            torch.cuda.current_stream().synchronize()
+            assert comm.error() == 0
+            out[rank] = (gp, sel)
+
+    _threads(G, body)
+    for gp, sel in out:
+        assert sel == sel1
+        for name in ("mean", "var", "l", "u"):
+            assert torch.equal(getattr(gp, name), getattr(one, name)), name
+        mine, ref = gp.cov, one.cov[:, gp.row0: gp.row0 + gp.n_loc]
+        if storage == "lower":
+            k = _kept(gp, cuda)
+            assert torch.equal(mine[:, k], ref[:, k])
+        else:
+            assert torch.equal(mine, ref)

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_sharded(cuda, G, domain, A, table, w, steps, conditioning, exchange="thread", storage="full"):
-    from talgp.dist import LocalPeerComm, ShardedITLBench, ThreadComm
+    from talgp.dist import LocalPeerComm, ThreadComm
+    from sharded_harness import ShardedITLBench
     if exchange == "peer":
         # the shards' kernels wait on each other while they share ONE GPU here: a cudaFree issued by the
         # caching allocator (device-wide synchronisation) in one thread would stall against a spinning

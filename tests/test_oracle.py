@@ -172,3 +172,33 @@ def test_step_uses_old_t_for_beta():
     seen.clear()
     model.step_idx(np.array([2]), np.array([[0.3]]), np.array([[0.1]]))
     assert set(seen) == {0} and model.t == 1
+
+
+def test_low_rank_replay_matches_dense_restatement():
+    """oracle/replay.py (the full-size checker: no N x N matrix) against the dense restatement of the
+    reference at a size where both run: means / variances / bounds to the last bits (same operations in the same
+    order), directed-ITL scores of a candidate subset to solver rounding."""
+    from oracle.replay import LowRankReplay
+    rng = np.random.default_rng(0)
+    N, m, T = 300, 40, 12
+    domain = rng.random((N, 3))
+    A = np.sort(rng.choice(N, m, replace=False))
+    kern = O.Matern52(lengthscale=0.3)
+    noise = O.HomoscedasticNoise(1, np.array([0.1]))
+    distrs = O.prior_distr(noise, domain, np.zeros((0, 3)), np.zeros((1, 0)), [kern], [O.ZeroMean()])
+    model = O.MarginalModel(0, domain, distrs, beta=np.array([1.5]), noise_rate=noise)
+    rep = LowRankReplay(kern, domain, 0.1, 1.5)
+    C = np.sort(rng.choice(N, 50, replace=False))
+    for t in range(T):
+        F = O.itl_directed(model, roi_idx=A)
+        np.testing.assert_allclose(rep.itl_directed(A, C), F[C], rtol=1e-6, atol=1e-9)
+        x = int(np.argmax(F)) if t % 3 else int(rng.integers(N))
+        y = float(rng.standard_normal())
+        model.step_idx(np.array([x]), np.array([[y]]), np.array([[0.1]]))
+        rep.observe(x, y)
+        # (LAPACK's 1 x 1 solve scales by a reciprocal where the replay divides: last-bit differences)
+        np.testing.assert_allclose(rep.var, model.variances[0], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(rep.mean, model.means[0], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(rep.l, model.l[0], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(rep.u, model.u[0], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(rep.block(A[:7], C), model.covariances[0][np.ix_(A[:7], C)], rtol=1e-12, atol=1e-15)

@@ -18,7 +18,9 @@ for p in (ROOT, os.path.join(ROOT, "transductive-active-learning_b200")):
     sys.path.insert(0, p)
 from bench import make_problem  # noqa: E402
 from talgp import _abi  # noqa: E402
-from talgp.dist import ShardedITLBench, default_comm  # noqa: E402
+from talgp.dist import default_comm  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from sharded_harness import ShardedITLBench  # noqa: E402
 from talgp.engine import DeviceGP  # noqa: E402
 
 

@@ -42,6 +42,9 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// dtype argument of the update entry points: TAL_F64 / TAL_F32, optionally | TAL_ARITH_FMA
+static inline int base_dtype(int dtype) { return dtype & ~TAL_ARITH_FMA; }
+static inline bool arith_fma(int dtype) { return (dtype & TAL_ARITH_FMA) != 0; }
 
 constexpr int kNumSM = 148;  // B200
 
@@ -59,6 +62,21 @@ __device__ __forceinline__ double sub_prod(double c, double a, double b) {
 }
 __device__ __forceinline__ float sub_prod(float c, float a, float b) {
   return __fsub_rn(c, __fmul_rn(a, b));
+}
+// Arithmetic mode of the covariance update (TAL_ARITH_FMA in the dtype argument of the update
+// entry points): FMA = false keeps the two roundings above; FMA = true is c - a*b with ONE
+// rounding (what a fused multiply-subtract loop computes), half the fp64 issue slots.  All
+// kernels that touch the matrix, the pending rows and the variance vector use the same mode,
+// so var == diag(cov) and deferred == per-step hold bit for bit in either mode.
+template <bool FMA>
+__device__ __forceinline__ double sub_prod_m(double c, double a, double b) {
+  if constexpr (FMA) return fma(-a, b, c);
+  else return __dsub_rn(c, __dmul_rn(a, b));
+}
+template <bool FMA>
+__device__ __forceinline__ float sub_prod_m(float c, float a, float b) {
+  if constexpr (FMA) return fmaf(-a, b, c);
+  else return __fsub_rn(c, __fmul_rn(a, b));
 }
 __device__ __forceinline__ double add_prod(double c, double a, double b) {
   return __dadd_rn(c, __dmul_rn(a, b));

@@ -38,10 +38,15 @@ cond_app_scalars_kernel(const double* __restrict__ col, i64 rows, i64 m_pad, con
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) {
     const i64 idx = idx_dev ? *idx_dev : idx_host;
+    if (idx < 0) {  // failed arg-max (idx = -1): two zero rows are appended, cs stays (scal2[2] = 0)
+      scal2[0] = 1.0; scal2[1] = 1.0; scal2[2] = 0.0;
+      return;
+    }
     const double r = rho[idx];
     const double kx = (double)kbuf[idx];
     scal2[0] = kx + acc + r * r;
     scal2[1] = (double)T(kx + r * r);  // as step_vectors_kernel
+    scal2[2] = 1.0;
   }
 }
 
@@ -88,7 +93,7 @@ cond_app_finish_kernel(double* __restrict__ Wb, i64 ldw, i64 rows, i64 ncols, i6
   const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= ncols) return;
   double g = 0.0, h = 0.0;
-  if (x < n_valid) {
+  if (x < n_valid && scal2[2] != 0.0) {
     const double k = (double)kbuf[cand0 + x], w = (double)wbuf[cand0 + x];
     double kA = k;
     for (int s = 0; s < n_split; ++s) kA += part[(i64)s * ncols + x];  // fixed order: deterministic

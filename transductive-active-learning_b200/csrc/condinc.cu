@@ -56,8 +56,8 @@ cond_coeffs_kernel(const double* __restrict__ pcol, i64 m_pad, const T* __restri
   __shared__ double wsum[32];
   __shared__ double carry_sh;
   const i64 idx = idx_dev ? *idx_dev : idx_host;
-  const double r = rho[idx];
-  const double s = (double)T((double)kbuf[idx] + r * r);  // as in step_vectors_kernel
+  const double r = idx >= 0 ? rho[idx] : 1.0;  // failed arg-max (idx = -1): pcol = 0, identity downdate
+  const double s = idx >= 0 ? (double)T((double)kbuf[idx] + r * r) : 1.0;  // as in step_vectors_kernel
   const double rs = sqrt(s);
   if (threadIdx.x == 0) carry_sh = 0.0;
   __syncthreads();

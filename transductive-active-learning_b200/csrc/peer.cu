@@ -19,60 +19,10 @@
 // is a fixed launch sequence (CUDA-graph capturable).  Spins are bounded
 // (kSpinTimeoutNs): on expiry the mailbox error word is set and the kernel
 // returns instead of hanging the GPU.
-#include "common.cuh"
+#include "peer.cuh"
 #include <cstring>
 
 namespace tal {
-
-constexpr int kPeerMax = TAL_PEER_MAX;
-constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
-
-struct alignas(64) PeerSlot {
-  tal_argmax_result rec;       // 32 B
-  unsigned long long seq;      // exchange number this record belongs to
-  unsigned long long pad[3];
-};
-
-struct alignas(256) PeerHeader {
-  unsigned long long rec_step;  // arg-max exchanges completed by THIS rank
-  unsigned long long row_step;  // row exchanges completed by THIS rank
-  unsigned long long pad1;
-  unsigned int ticket;          // last-block election of the push kernel
-  int error;                    // != 0: a spin timed out (TAL_PEER_ERR_*)
-  unsigned long long pad0[4];
-  unsigned long long ready[kPeerMax];    // ready[g] = s: rank g may receive row exchange s
-  unsigned long long row_seq[kPeerMax];  // row_seq[g] = s: rank g's piece of exchange s has landed here
-  PeerSlot slot[2][kPeerMax];
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long now_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-// spin until *p >= want (the counters only grow; a peer without a piece may already
-// have announced the next exchange); false on timeout
-__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long want) {
-  if (ld_acquire_sys(p) >= want) return true;
-  const unsigned long long t0 = now_ns();
-  for (;;) {
-    for (int i = 0; i < 64; ++i)
-      if (ld_acquire_sys(p) >= want) return true;
-    if (now_ns() - t0 > kSpinTimeoutNs) return false;
-    __nanosleep(100);
-  }
-}
-
-__device__ __forceinline__ PeerHeader* hdr(void* mailbox) { return reinterpret_cast<PeerHeader*>(mailbox); }
 
 // ---- arg-max all-gather ----------------------------------------------------
 // One warp: lane g publishes this rank's record to peer g.
@@ -95,43 +45,9 @@ __global__ void peer_publish_kernel(const tal_argmax_result* __restrict__ rec, v
 __global__ void peer_combine_kernel(void* mailbox, int G, tal_argmax_result* __restrict__ out) {
   PeerHeader* h = hdr(mailbox);
   const unsigned long long s = h->rec_step + 1;
-  const int g = threadIdx.x;
-  double val = -INFINITY;
-  i64 idx = 0x7fffffffffffffffLL, cnt = 0;
-  int flags = 0;
-  bool ok = true;
-  if (g < G) {
-    PeerSlot* sl = &h->slot[s & 1][g];
-    ok = spin_until(&sl->seq, s);
-    const volatile tal_argmax_result* r = &sl->rec;
-    val = r->val; idx = r->idx; cnt = r->n_ties; flags = r->flags;
-    if (cnt == 0) { val = -INFINITY; idx = 0x7fffffffffffffffLL; }
-  }
-  if (!__all_sync(0xffffffffu, ok)) {
-    if (g == 0) h->error = TAL_PEER_ERR_RECORD_TIMEOUT;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double v2 = __shfl_xor_sync(0xffffffffu, val, o);
-    const i64 i2 = __shfl_xor_sync(0xffffffffu, idx, o);
-    const i64 c2 = __shfl_xor_sync(0xffffffffu, cnt, o);
-    const int f2 = __shfl_xor_sync(0xffffffffu, flags, o);
-    flags |= f2;
-    if (c2 == 0 || (cnt != 0 && val > v2)) {
-    } else if (cnt == 0 || v2 > val) {
-      val = v2; idx = i2; cnt = c2;
-    } else {
-      idx = idx < i2 ? idx : i2; cnt += c2;
-    }
-  }
-  if (g == 0) {
-    out->idx = cnt ? idx : -1;
-    out->val = val;
-    out->n_ties = cnt;
-    out->flags = flags;
-    out->status = !(flags & 1) ? TAL_ARGMAX_EMPTY_SAFE_SET
-                  : !(flags & 2) ? TAL_ARGMAX_ALL_NEG_INF
-                  : !(flags & 4) ? TAL_ARGMAX_ALL_NAN : TAL_ARGMAX_OK;
+  const tal_argmax_result r = combine_records_warp(h, s, G);
+  if (threadIdx.x == 0) {
+    *out = r;
     h->rec_step = s;
   }
 }
@@ -152,22 +68,46 @@ struct ShardBounds {
   i64 b[kPeerMax + 1];  // rank g holds global rows [b[g], b[g + 1])
 };
 
-template <typename T>
+// COMBINE: the arg-max records of this step were published (fused.cu, last block of the select
+// pass) but not yet combined: every block waits for the G records and reduces them itself (the
+// index of the row is their result), block (0,0,0) writes the combined record and scal[i] =
+// mean[i][idx], the last block to finish advances rec_step.
+template <typename T, bool COMBINE>
 __global__ void __launch_bounds__(256)
 peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBounds bounds,
                      const T* __restrict__ cov, i64 stride_q, i64 ld, i64 N, i64 sym_block,
-                     const i64* __restrict__ idx_dev, i64 idx_host,
+                     const i64* __restrict__ idx_dev, i64 idx_host, tal_argmax_result* __restrict__ combined,
+                     const double* __restrict__ mean, double* __restrict__ scal, int q,
                      i64 kbuf_off,  // byte offset of kbuf [q][ld] inside a mailbox
                      const double* __restrict__ V, i64 v_stride_q, i64 ldv, i64 m_pad,
-                     i64 pcol_off,  // byte offset of pcol [q][m_pad] inside a mailbox (V != null)
+                     i64 pcol_off,  // byte offset of pcol [q][pcol_stride] inside a mailbox (V != null)
+                     i64 pcol_stride,  // doubles between the GPs' columns in the mailbox (>= m_pad)
                      i64 cand0, i64 n_cand) {  // V holds columns (candidates) [cand0, cand0 + n_cand)
   typedef typename Vec16<T>::type V16;
   constexpr int VN = Vec16<T>::n;
   __shared__ bool s_last;
+  __shared__ i64 s_idx;
   const int gp = blockIdx.y;
-  i64 idx = idx_dev ? *idx_dev : idx_host;
-  if (idx < 0 || idx >= N) idx = -1;  // failed arg-max: zeros are exchanged, the protocol keeps moving
   PeerHeader* me = hdr(boxes[rank]);
+  i64 idx;
+  unsigned long long s_rec = 0;
+  if constexpr (COMBINE) {
+    s_rec = me->rec_step + 1;
+    if (threadIdx.x < 32) {
+      const tal_argmax_result r = combine_records_warp(me, s_rec, G);
+      if (threadIdx.x == 0) {
+        s_idx = r.idx;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *combined = r;
+      }
+    }
+    __syncthreads();
+    idx = s_idx;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (int)threadIdx.x < q && idx >= 0 && idx < N)
+      scal[threadIdx.x] = mean[(i64)threadIdx.x * N + idx];
+  } else {
+    idx = idx_dev ? *idx_dev : idx_host;
+  }
+  if (idx < 0 || idx >= N) idx = -1;  // failed arg-max: zeros are exchanged, the protocol keeps moving
   const unsigned long long s = me->row_step + 1;
   if (blockIdx.x == 0 && gp == 0 && blockIdx.z == 0 && (int)threadIdx.x < G)
     st_release_sys(&hdr(boxes[threadIdx.x])->ready[rank], s);
@@ -208,7 +148,7 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
     char* box = reinterpret_cast<char*>(boxes[g]);
     if (mine) *reinterpret_cast<V16*>(reinterpret_cast<T*>(box + kbuf_off) + (i64)gp * ld + base) = v;
     if (col_mine)
-      reinterpret_cast<double*>(box + pcol_off)[(i64)gp * m_pad + t] =
+      reinterpret_cast<double*>(box + pcol_off)[(i64)gp * pcol_stride + t] =
           own_col ? V[gp * v_stride_q + t * ldv + (idx - cand0)] : 0.0;
     __threadfence_system();
   }
@@ -222,7 +162,10 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
   if (!s_last) return;
   if ((int)threadIdx.x < G) {
     __threadfence_system();
-    if (threadIdx.x == 0) me->ticket = 0;
+    if (threadIdx.x == 0) {
+      me->ticket = 0;
+      if constexpr (COMBINE) me->rec_step = s_rec;  // every block has read it by now
+    }
     st_release_sys(&hdr(boxes[threadIdx.x])->row_seq[rank], s);
   }
 }
@@ -244,6 +187,43 @@ __global__ void peer_wait_row_kernel(void* mailbox, int G, const i64* __restrict
 }
 
 static i64 align_up(i64 x, i64 a) { return (x + a - 1) / a * a; }
+
+}  // namespace tal
+
+namespace tal {
+
+// combined != null: the records of this step are combined inside the kernel (see the kernel).
+int peer_push_row_impl(void* const* mailboxes, int G, int rank, const long long* bounds_host, const void* cov,
+                       long long cov_stride_q, long long ld, long long N, int q, int lower,
+                       const long long* idx_dev, long long idx_host, long long kbuf_off, const double* V,
+                       long long v_stride_q, long long ldv, long long m_pad, long long pcol_off,
+                       long long pcol_stride, long long cand0, long long n_cand, int dtype,
+                       tal_argmax_result* combined, const double* mean, double* scal, void* stream) {
+  TAL_ARG(mailboxes && cov && bounds_host && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
+  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= N && N >= 1 && ld % 4 == 0);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(kbuf_off >= (long long)sizeof(PeerHeader) && kbuf_off % 16 == 0);
+  TAL_ARG(V == nullptr || (m_pad >= 1 && pcol_off % 16 == 0 && pcol_stride >= m_pad));
+  TAL_ARG(combined == nullptr || (mean && scal));
+  ShardBounds bounds;
+  for (int g = 0; g <= kPeerMax; ++g) bounds.b[g] = g <= G ? bounds_host[g] : bounds_host[G];
+  TAL_ARG(bounds.b[0] == 0 && bounds.b[G] == N);
+  for (int g = 0; g < G; ++g) TAL_ARG(bounds.b[g] <= bounds.b[g + 1] && bounds.b[g] % 4 == 0);
+  const i64 vn = dtype == TAL_F64 ? 2 : 4;
+  const i64 blk = lower ? tal_sym_block(dtype) : 0;
+  i64 span = (ld + vn - 1) / vn;
+  if (V && m_pad > span) span = m_pad;
+  dim3 grid((unsigned)((span + 255) / 256), q, G);
+#define TAL_PUSH(T, C)                                                                              \
+  peer_push_row_kernel<T, C><<<grid, 256, 0, as_stream(stream)>>>(                                  \
+      mailboxes, G, rank, bounds, (const T*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host, combined, mean, \
+      scal, q, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, pcol_stride, cand0, n_cand)
+  if (dtype == TAL_F64) { if (combined) TAL_PUSH(double, true); else TAL_PUSH(double, false); }
+  else { if (combined) TAL_PUSH(float, true); else TAL_PUSH(float, false); }
+#undef TAL_PUSH
+  TAL_LAUNCH_CHECK("tal_peer_push_row");
+  return TAL_OK;
+}
 
 }  // namespace tal
 
@@ -329,31 +309,11 @@ int tal_peer_push_row(void* const* mailboxes, int G, int rank, const long long* 
                       long long cov_stride_q, long long ld, long long N, int q, int lower,
                       const long long* idx_dev, long long idx_host, long long kbuf_off,
                       const double* V, long long v_stride_q, long long ldv, long long m_pad,
-                      long long pcol_off, long long cand0, long long n_cand, int dtype, void* stream) {
-  TAL_ARG(mailboxes && cov && bounds_host && G >= 1 && G <= kPeerMax && rank >= 0 && rank < G);
-  TAL_ARG(q >= 1 && q <= TAL_MAX_Q && ld >= N && N >= 1 && ld % 4 == 0);
-  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
-  TAL_ARG(kbuf_off >= (long long)sizeof(PeerHeader) && kbuf_off % 16 == 0);
-  TAL_ARG(V == nullptr || (m_pad >= 1 && pcol_off % 16 == 0));
-  ShardBounds bounds;
-  for (int g = 0; g <= kPeerMax; ++g) bounds.b[g] = g <= G ? bounds_host[g] : bounds_host[G];
-  TAL_ARG(bounds.b[0] == 0 && bounds.b[G] == N);
-  for (int g = 0; g < G; ++g) TAL_ARG(bounds.b[g] <= bounds.b[g + 1] && bounds.b[g] % 4 == 0);
-  const i64 vn = dtype == TAL_F64 ? 2 : 4;
-  const i64 blk = lower ? tal_sym_block(dtype) : 0;
-  i64 span = (ld + vn - 1) / vn;
-  if (V && m_pad > span) span = m_pad;
-  dim3 grid((unsigned)((span + 255) / 256), q, G);
-  if (dtype == TAL_F64)
-    peer_push_row_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
-        mailboxes, G, rank, bounds, (const double*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
-        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, cand0, n_cand);
-  else
-    peer_push_row_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
-        mailboxes, G, rank, bounds, (const float*)cov, cov_stride_q, ld, N, blk, idx_dev, idx_host,
-        kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, cand0, n_cand);
-  TAL_LAUNCH_CHECK("tal_peer_push_row");
-  return TAL_OK;
+                      long long pcol_off, long long pcol_stride, long long cand0, long long n_cand, int dtype,
+                      void* stream) {
+  return tal::peer_push_row_impl(mailboxes, G, rank, bounds_host, cov, cov_stride_q, ld, N, q, lower, idx_dev,
+                                 idx_host, kbuf_off, V, v_stride_q, ldv, m_pad, pcol_off, pcol_stride, cand0,
+                                 n_cand, dtype, nullptr, nullptr, nullptr, stream);
 }
 
 int tal_peer_wait_row(void* mailbox, int G, const long long* idx_dev, long long idx_host, const double* mean,

@@ -37,7 +37,7 @@ extract_row_kernel(const T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i6
     if (own) v = cov[gp * stride_q + r * ld + col];
     kbuf[(i64)gp * ld + col] = v;
   }
-  if (col == 0) scal[gp] = mean[(i64)gp * N + idx];
+  if (col == 0 && idx >= 0 && idx < N) scal[gp] = mean[(i64)gp * N + idx];
 }
 
 __global__ void stash_mean_kernel(const double* __restrict__ mean, i64 N, int q,
@@ -49,7 +49,7 @@ __global__ void stash_mean_kernel(const double* __restrict__ mean, i64 N, int q,
 // --------------------------------------------------------------------------
 // Phase 2: the O(qN) state: w, mean, var, l, u.
 // --------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool FMA>
 __global__ void __launch_bounds__(256)
 step_vectors_kernel(const T* __restrict__ kbuf, T* __restrict__ wbuf, i64 N, i64 ld,
                     const i64* __restrict__ idx_dev, i64 idx_host,
@@ -61,6 +61,10 @@ step_vectors_kernel(const T* __restrict__ kbuf, T* __restrict__ wbuf, i64 N, i64
   const i64 idx = idx_dev ? *idx_dev : idx_host;
   const i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= ld) return;
+  if (idx < 0 || idx >= N) {  // failed arg-max (idx = -1): the observation is a no-op (k = 0 from the
+    wbuf[(i64)gp * ld + b] = T(0);  // row extract, w = 0: a queued update changes nothing)
+    return;
+  }
   const T* k = kbuf + (i64)gp * ld;
   // Sigma = cov[idx, idx] + noise_std^2 (gaussian_distribution.py:29-32); the
   // arithmetic is done in T so that var stays bit-identical to diag(cov).
@@ -75,7 +79,7 @@ step_vectors_kernel(const T* __restrict__ kbuf, T* __restrict__ wbuf, i64 N, i64
   const double delta = yv - scal[gp];  // obs - prior_mean[obs_idx] (:120)
   const i64 o = (i64)gp * N + b;
   const double m_new = add_prod(mean[o], (double)wb, delta);
-  const T v_new = sub_prod(T(var[o]), kb, wb);  // == diag of the matrix update
+  const T v_new = sub_prod_m<FMA>(T(var[o]), kb, wb);  // == diag of the matrix update
   mean[o] = m_new;
   var[o] = (double)v_new;
   const double sd = sqrt((double)v_new);  // NaN for negative variance, as the reference
@@ -89,7 +93,7 @@ step_vectors_kernel(const T* __restrict__ kbuf, T* __restrict__ wbuf, i64 N, i64
 // --------------------------------------------------------------------------
 
 // Variant 1: 16-byte LDG/STG, UNROLL independent rows in flight per thread.
-template <typename T, int UNROLL>
+template <typename T, int UNROLL, bool FMA>
 __global__ void __launch_bounds__(256)
 rank1_ldg16_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
                    const T* __restrict__ kbuf, const T* __restrict__ wbuf, int rows_per_cta) {
@@ -117,13 +121,13 @@ rank1_ldg16_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_lo
     for (int j = 0; j < UNROLL; ++j) {
       if (r + j < r1) {
         if constexpr (VN == 2) {
-          c[j].x = sub_prod(c[j].x, kk[j], wv.x);
-          c[j].y = sub_prod(c[j].y, kk[j], wv.y);
+          c[j].x = sub_prod_m<FMA>(c[j].x, kk[j], wv.x);
+          c[j].y = sub_prod_m<FMA>(c[j].y, kk[j], wv.y);
         } else {
-          c[j].x = sub_prod(c[j].x, kk[j], wv.x);
-          c[j].y = sub_prod(c[j].y, kk[j], wv.y);
-          c[j].z = sub_prod(c[j].z, kk[j], wv.z);
-          c[j].w = sub_prod(c[j].w, kk[j], wv.w);
+          c[j].x = sub_prod_m<FMA>(c[j].x, kk[j], wv.x);
+          c[j].y = sub_prod_m<FMA>(c[j].y, kk[j], wv.y);
+          c[j].z = sub_prod_m<FMA>(c[j].z, kk[j], wv.z);
+          c[j].w = sub_prod_m<FMA>(c[j].w, kk[j], wv.w);
         }
         st_stream(reinterpret_cast<V*>(C + (r + j) * ld), c[j]);
       }
@@ -177,7 +181,7 @@ struct Vec32<float> {
   static constexpr int n = 8;
 };
 
-template <typename T, int UNROLL>
+template <typename T, int UNROLL, bool FMA>
 __global__ void __launch_bounds__(256)
 rank1_ldg32_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
                    const T* __restrict__ kbuf, const T* __restrict__ wbuf, int rows_per_cta,
@@ -212,7 +216,7 @@ rank1_ldg32_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_lo
     for (int j = 0; j < UNROLL; ++j) {
       if (r + j < r1) {
 #pragma unroll
-        for (int e = 0; e < VN; ++e) c[j].v[e] = sub_prod(c[j].v[e], kk[j], wv.v[e]);
+        for (int e = 0; e < VN; ++e) c[j].v[e] = sub_prod_m<FMA>(c[j].v[e], kk[j], wv.v[e]);
         st256(C + (r + j) * ld, c[j]);
       }
     }
@@ -271,7 +275,7 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <typename T, int SEG_BYTES, int STAGES, int THREADS>
+template <typename T, int SEG_BYTES, int STAGES, int THREADS, bool FMA>
 __global__ void __launch_bounds__(THREADS)
 rank1_bulk_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc,
                   const T* __restrict__ kbuf, const T* __restrict__ wbuf, int rows_per_cta) {
@@ -327,13 +331,13 @@ rank1_bulk_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc
       if (v < seg_vecs) {
         V c = sv[v];
         if constexpr (VN == 2) {
-          c.x = sub_prod(c.x, kk, wv[j].x);
-          c.y = sub_prod(c.y, kk, wv[j].y);
+          c.x = sub_prod_m<FMA>(c.x, kk, wv[j].x);
+          c.y = sub_prod_m<FMA>(c.y, kk, wv[j].y);
         } else {
-          c.x = sub_prod(c.x, kk, wv[j].x);
-          c.y = sub_prod(c.y, kk, wv[j].y);
-          c.z = sub_prod(c.z, kk, wv[j].z);
-          c.w = sub_prod(c.w, kk, wv[j].w);
+          c.x = sub_prod_m<FMA>(c.x, kk, wv[j].x);
+          c.y = sub_prod_m<FMA>(c.y, kk, wv[j].y);
+          c.z = sub_prod_m<FMA>(c.z, kk, wv[j].z);
+          c.w = sub_prod_m<FMA>(c.w, kk, wv[j].w);
         }
         sv[v] = c;
       }
@@ -554,27 +558,28 @@ int tal_step_vectors(const void* kbuf, void* wbuf, long long N, int q, const lon
                      double* mean, double* var, double* l, double* u, int dtype, void* stream) {
   TAL_ARG(kbuf && wbuf && y_dev && rho && beta_host && scal && mean && var && l && u);
   TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   BetaQ beta;
   for (int i = 0; i < TAL_MAX_Q; ++i) beta.v[i] = i < q ? beta_host[i] : 0.0;
   // kbuf / wbuf rows are `ld` elements apart, ld = N rounded up to 32
   const i64 ld = (N + 31) / 32 * 32;
   dim3 grid((unsigned)((ld + 255) / 256), q);
-  if (dtype == TAL_F64)
-    step_vectors_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
-        (const double*)kbuf, (double*)wbuf, N, ld, idx_dev, idx_host, y_dev, y_stride, y_gather,
-        rho, beta, scal, mean, var, l, u);
-  else
-    step_vectors_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
-        (const float*)kbuf, (float*)wbuf, N, ld, idx_dev, idx_host, y_dev, y_stride, y_gather,
-        rho, beta, scal, mean, var, l, u);
+#define TAL_SV(T, F)                                                                              \
+  step_vectors_kernel<T, F><<<grid, 256, 0, as_stream(stream)>>>(                                 \
+      (const T*)kbuf, (T*)wbuf, N, ld, idx_dev, idx_host, y_dev, y_stride, y_gather, rho, beta,   \
+      scal, mean, var, l, u)
+  if (dtype == TAL_F64) { if (fma_mode) TAL_SV(double, true); else TAL_SV(double, false); }
+  else { if (fma_mode) TAL_SV(float, true); else TAL_SV(float, false); }
+#undef TAL_SV
   TAL_LAUNCH_CHECK("tal_step_vectors");
   return TAL_OK;
 }
 
 }  // extern "C"
 
-template <typename T>
+template <typename T, bool FMA>
 static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* kbuf,
                         const T* wbuf, int variant, cudaStream_t st, i64 sym_block = 0) {
   if (n_loc == 0) return TAL_OK;
@@ -584,7 +589,7 @@ static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
     const int rows_per_cta = 64;
     dim3 grid((unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta),
               (unsigned)((ld + 256 * VN - 1) / (256 * VN)), q);
-    rank1_ldg16_kernel<T, 8><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, kbuf, wbuf,
+    rank1_ldg16_kernel<T, 8, FMA><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, kbuf, wbuf,
                                                    rows_per_cta);
   } else if (variant == 3) {
     constexpr int VN = Vec32<T>::n;
@@ -596,18 +601,18 @@ static int launch_rank1(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
       TAL_ARG(row_blocks <= 65535);
     }
     dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
-    rank1_ldg32_kernel<T, 4><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, kbuf, wbuf,
+    rank1_ldg32_kernel<T, 4, FMA><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, kbuf, wbuf,
                                                    rows_per_cta, sym_block);
   } else if (variant == 2) {
     constexpr int SEG = 8192, STAGES = 6, THREADS = 256;
     constexpr int SEG_ELEMS = SEG / (int)sizeof(T);
     const int rows_per_cta = 128;
     const size_t smem = (size_t)STAGES * SEG + STAGES * sizeof(uint64_t);
-    static bool attr_done[2] = {false, false};
-    auto kern = rank1_bulk_kernel<T, SEG, STAGES, THREADS>;
-    if (!attr_done[sizeof(T) == 8]) {
+    static bool attr_done = false;  // (one flag per instantiation of this function template)
+    auto kern = rank1_bulk_kernel<T, SEG, STAGES, THREADS, FMA>;
+    if (!attr_done) {
       TAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done[sizeof(T) == 8] = true;
+      attr_done = true;
     }
     dim3 grid((unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta),
               (unsigned)((ld + SEG_ELEMS - 1) / SEG_ELEMS), q);
@@ -628,13 +633,16 @@ int tal_rank1_update(void* cov, long long cov_stride_q, long long ld, long long 
   TAL_ARG(cov && kbuf && wbuf);
   TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld >= N && ld % 32 == 0 && n_loc >= 0);
   TAL_ARG(ld == (N + 31) / 32 * 32);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
-  if (dtype == TAL_F64)
-    return launch_rank1<double>((double*)cov, cov_stride_q, ld, row0, n_loc, q,
-                                (const double*)kbuf, (const double*)wbuf, variant,
-                                as_stream(stream));
-  return launch_rank1<float>((float*)cov, cov_stride_q, ld, row0, n_loc, q, (const float*)kbuf,
-                             (const float*)wbuf, variant, as_stream(stream));
+#define TAL_R1(T, F)                                                                               \
+  return launch_rank1<T, F>((T*)cov, cov_stride_q, ld, row0, n_loc, q, (const T*)kbuf, (const T*)wbuf, \
+                            variant, as_stream(stream))
+  if (dtype == TAL_F64) { if (fma_mode) TAL_R1(double, true); TAL_R1(double, false); }
+  if (fma_mode) TAL_R1(float, true);
+  TAL_R1(float, false);
+#undef TAL_R1
 }
 
 int tal_gather_rows(const void* cov, long long ld, long long row0, long long n_loc, long long N,
@@ -700,13 +708,17 @@ int tal_rank1_update_lower(void* cov, long long cov_stride_q, long long ld, long
                            int dtype, void* stream) {
   TAL_ARG(cov && kbuf && wbuf);
   TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld == (N + 31) / 32 * 32 && n_loc >= 0);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   const i64 blk = tal_sym_block(dtype);
-  if (dtype == TAL_F64)
-    return launch_rank1<double>((double*)cov, cov_stride_q, ld, row0, n_loc, q, (const double*)kbuf,
-                                (const double*)wbuf, 3, as_stream(stream), blk);
-  return launch_rank1<float>((float*)cov, cov_stride_q, ld, row0, n_loc, q, (const float*)kbuf,
-                             (const float*)wbuf, 3, as_stream(stream), blk);
+#define TAL_R1(T, F)                                                                               \
+  return launch_rank1<T, F>((T*)cov, cov_stride_q, ld, row0, n_loc, q, (const T*)kbuf, (const T*)wbuf, \
+                            3, as_stream(stream), blk)
+  if (dtype == TAL_F64) { if (fma_mode) TAL_R1(double, true); TAL_R1(double, false); }
+  if (fma_mode) TAL_R1(float, true);
+  TAL_R1(float, false);
+#undef TAL_R1
 }
 
 int tal_extract_row_lower(const void* cov, long long cov_stride_q, long long ld, long long row0,

@@ -17,6 +17,7 @@
 // the result is bit-identical.  The pass stays HBM-bound up to b ~ 16
 // (2 b flops per 16 bytes against 33.8 TFLOP/s of fp64 FMA issue).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace tal {
 
@@ -46,8 +47,9 @@ struct Lanes {
 // grid: full storage (row blocks, column tiles, q); lower storage (column tiles, row blocks, q).
 // K, W: [P][q][ld] pending vectors (zero-padded beyond the p in use).  ROWS rows per CTA; the
 // CTA's K values are staged in shared memory ([P][ROWS]), every thread keeps its P w-vectors in
-// registers and has UNROLL rows of loads in flight.
-template <typename T, int P, int UNROLL>
+// registers and has UNROLL rows of loads in flight.  PIPE: the loads of the next UNROLL rows are
+// issued before the arithmetic of the current ones (2 x UNROLL rows in flight per thread).
+template <typename T, int P, int UNROLL, bool FMA, bool PIPE>
 __global__ void __launch_bounds__(256, 2)
 rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, const T* __restrict__ K,
              const T* __restrict__ W, i64 pend_stride, int rows_per_cta, i64 sym_block) {
@@ -75,14 +77,15 @@ rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, con
     memcpy(&wv[i], &t, sizeof(V));
   }
   T* C = cov + gp * stride_q + col;
-  for (i64 r = r0; r < r1; r += UNROLL) {
-    Lanes<T, VN> c[UNROLL];
+  auto load_rows = [&](Lanes<T, VN>* c, i64 r) {
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j)
       if (r + j < r1) {
         const V t = ld_stream(reinterpret_cast<const V*>(C + (r + j) * ld));
         memcpy(&c[j], &t, sizeof(V));
       }
+  };
+  auto update_rows = [&](Lanes<T, VN>* c, i64 r) {
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j)
       if (r + j < r1) {
@@ -90,19 +93,35 @@ rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, con
         for (int i = 0; i < P; ++i) {
           const T kk = ksm[i][r + j - r0];
 #pragma unroll
-          for (int e = 0; e < VN; ++e) c[j].v[e] = sub_prod(c[j].v[e], kk, wv[i].v[e]);
+          for (int e = 0; e < VN; ++e) c[j].v[e] = sub_prod_m<FMA>(c[j].v[e], kk, wv[i].v[e]);
         }
         V t;
         memcpy(&t, &c[j], sizeof(V));
         st_stream(reinterpret_cast<V*>(C + (r + j) * ld), t);
       }
+  };
+  if constexpr (!PIPE) {
+    for (i64 r = r0; r < r1; r += UNROLL) {
+      Lanes<T, VN> c[UNROLL];
+      load_rows(c, r);
+      update_rows(c, r);
+    }
+  } else {
+    Lanes<T, VN> a[UNROLL], b[UNROLL];
+    load_rows(a, r0);
+    for (i64 r = r0; r < r1; r += 2 * UNROLL) {
+      load_rows(b, r + UNROLL);
+      update_rows(a, r);
+      load_rows(a, r + 2 * UNROLL);
+      update_rows(b, r + UNROLL);
+    }
   }
 }
 
 // k[c] <- (((k[c] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ...) with (a, b) = (x, c) for the entries the row
 // x keeps and (c, x) for the mirrored ones (lower-block storage): exactly what the deferred passes
 // will do to those entries.  grid (ceil(ld / 256), q).
-template <typename T>
+template <typename T, bool FMA>
 __global__ void __launch_bounds__(256)
 pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict__ K, const T* __restrict__ W,
                        i64 pend_stride, int p, const i64* __restrict__ idx_dev, i64 idx_host, i64 sym_block) {
@@ -116,32 +135,50 @@ pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict_
   for (int i = 0; i < p; ++i) {
     const T* Ki = K + (i64)i * pend_stride + (i64)gp * ld;
     const T* Wi = W + (i64)i * pend_stride + (i64)gp * ld;
-    v = mirrored ? sub_prod(v, Ki[c], Wi[x]) : sub_prod(v, Ki[x], Wi[c]);
+    v = mirrored ? sub_prod_m<FMA>(v, Ki[c], Wi[x]) : sub_prod_m<FMA>(v, Ki[x], Wi[c]);
   }
   kbuf[(i64)gp * ld + c] = v;
 }
 
-template <typename T, int P>
+// Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = 0 (default: UNROLL 4 at P = 16, 8 below),
+// 1 (UNROLL 8 everywhere), 2 (software-pipelined, 2 x 4 rows in flight), 3 (pipelined, 2 x 2).
+static int rankb_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAL_RANKB_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <typename T, int P, bool FMA>
 static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
                         i64 pend_stride, i64 sym_block, cudaStream_t st) {
   constexpr int VN = VecB<T>::n;
-  constexpr int UNROLL = P >= 16 ? 4 : 8;  // P w-vectors + UNROLL rows in registers: 2 CTAs per SM
   const int rows_per_cta = 32;
   const unsigned row_blocks = (unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta);
   const unsigned col_tiles = (unsigned)((ld + 256 * VN - 1) / (256 * VN));
   dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
-  rankb_kernel<T, P, UNROLL><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride,
-                                                   rows_per_cta, sym_block);
+#define TAL_RB(U, PIPE)                                                                            \
+  rankb_kernel<T, P, U, FMA, PIPE><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, \
+                                                         rows_per_cta, sym_block)
+  const int v = rankb_variant();
+  if (v == 1) TAL_RB(8, false);
+  else if (v == 2) TAL_RB(4, true);
+  else if (v == 3) TAL_RB(2, true);
+  else if (P >= 16) TAL_RB(4, false);  // P w-vectors + UNROLL rows in registers: 2 CTAs per SM
+  else TAL_RB(8, false);
+#undef TAL_RB
   return 0;
 }
 
-template <typename T>
+template <typename T, bool FMA>
 static int rankb_dispatch(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
                           i64 pend_stride, int p, i64 sym_block, cudaStream_t st) {
-  if (p <= 2) return launch_rankb<T, 2>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  if (p <= 4) return launch_rankb<T, 4>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  if (p <= 8) return launch_rankb<T, 8>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  return launch_rankb<T, 16>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 2) return launch_rankb<T, 2, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 4) return launch_rankb<T, 4, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 8) return launch_rankb<T, 8, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  return launch_rankb<T, 16, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
 }
 
 }  // namespace tal
@@ -156,18 +193,20 @@ int tal_rankb_update(void* cov, long long cov_stride_q, long long ld, long long 
   TAL_ARG(cov && K && W);
   TAL_ARG(q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld == (N + 31) / 32 * 32 && n_loc >= 0);
   TAL_ARG(p >= 1 && p <= TAL_MAX_PENDING && pend_stride >= (long long)q * ld);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   TAL_ARG(row0 % 32 == 0);
   if (n_loc == 0) return TAL_OK;
   const i64 blk = lower ? tal_sym_block(dtype) : 0;
   const unsigned row_blocks = (unsigned)((n_loc + 31) / 32);
   if (lower) TAL_ARG(row_blocks <= 65535);
-  if (dtype == TAL_F64)
-    rankb_dispatch<double>((double*)cov, cov_stride_q, ld, row0, n_loc, q, (const double*)K, (const double*)W,
-                           pend_stride, p, blk, as_stream(stream));
-  else
-    rankb_dispatch<float>((float*)cov, cov_stride_q, ld, row0, n_loc, q, (const float*)K, (const float*)W,
-                          pend_stride, p, blk, as_stream(stream));
+#define TAL_RBD(T, F)                                                                             \
+  rankb_dispatch<T, F>((T*)cov, cov_stride_q, ld, row0, n_loc, q, (const T*)K, (const T*)W, pend_stride, p, blk, \
+                       as_stream(stream))
+  if (dtype == TAL_F64) { if (fma_mode) TAL_RBD(double, true); else TAL_RBD(double, false); }
+  else { if (fma_mode) TAL_RBD(float, true); else TAL_RBD(float, false); }
+#undef TAL_RBD
   TAL_LAUNCH_CHECK("tal_rankb_update");
   return TAL_OK;
 }
@@ -177,16 +216,18 @@ int tal_pending_correct_row(void* kbuf, long long ld, long long N, int q, const 
                             int lower, int dtype, void* stream) {
   TAL_ARG(kbuf && K && W && q >= 1 && q <= TAL_MAX_Q && N >= 1 && ld >= N);
   TAL_ARG(p >= 0 && p <= TAL_MAX_PENDING);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   if (p == 0) return TAL_OK;
   const i64 blk = lower ? tal_sym_block(dtype) : 0;
   dim3 grid((unsigned)((ld + 255) / 256), q);
-  if (dtype == TAL_F64)
-    pending_correct_kernel<double><<<grid, 256, 0, as_stream(stream)>>>(
-        (double*)kbuf, ld, N, (const double*)K, (const double*)W, pend_stride, p, idx_dev, idx_host, blk);
-  else
-    pending_correct_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
-        (float*)kbuf, ld, N, (const float*)K, (const float*)W, pend_stride, p, idx_dev, idx_host, blk);
+#define TAL_PC(T, F)                                                                              \
+  pending_correct_kernel<T, F><<<grid, 256, 0, as_stream(stream)>>>((T*)kbuf, ld, N, (const T*)K, (const T*)W, \
+                                                                   pend_stride, p, idx_dev, idx_host, blk)
+  if (dtype == TAL_F64) { if (fma_mode) TAL_PC(double, true); else TAL_PC(double, false); }
+  else { if (fma_mode) TAL_PC(float, true); else TAL_PC(float, false); }
+#undef TAL_PC
   TAL_LAUNCH_CHECK("tal_pending_correct_row");
   return TAL_OK;
 }

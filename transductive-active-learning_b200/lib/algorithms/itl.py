@@ -17,13 +17,43 @@ class ITL(DirectedDiscreteGreedyAlgorithm):
         assert conditioning in ("auto", "recompute", "incremental")
         self.conditioning = conditioning
 
+    gather_F = True  # row-sharded model: result["F"] is all-gathered to full length (one NCCL call per step)
+
+    def _incremental(self, roi) -> bool:
+        return self.conditioning == "incremental" or (self.conditioning == "auto" and roi.fixed)
+
+    def _step(self, f, update_model: bool = True):
+        """The greedy step (lib/algorithms/__init__.py:77-94).  With a resident conditioning state
+        for a fixed ROI the selection of this step was already made by the fused kernels of the
+        previous observation (csrc/fused.cu): the host reads the 32-byte record, asks the black box,
+        and issues ONE call for the update + the next selection."""
+        model, gp = self.model, self.model._gp
+        st = gp._cond
+        if update_model and st is not None and st["valid"] and st["append"] and gp._ctx_usable():
+            roi = self.roi
+            if st["key"] is roi and self._incremental(roi) and not model.safe_set_is_subset_of(A=roi):
+                rec = gp.ctx_select(model.first_constraint, model._safe_override(), self.sample_mask())
+                idx = model._check_argmax(gp.read_result(rec))
+                F = gp._scratch("ctx_F", (gp.n_cand,)).clone()  # (the update below overwrites it with the next scores)
+                if gp.sharded and self.gather_F:
+                    F = gp.gather_candidates(F)
+                X = model.domain[idx: idx + 1]
+                y = f.observe(X)
+                model._step_index(rec[0:1], y, auto_select=True)
+                if not isinstance(y, torch.Tensor):
+                    import numpy as np
+                    y = torch.as_tensor(np.asarray(y, dtype=np.float64))
+                i_loc = idx - (gp.cand0 if (gp.sharded and F.numel() != model.n) else 0)
+                F_max = F[i_loc] if 0 <= i_loc < F.numel() else torch.as_tensor(float(model.last_argmax.val))
+                return X, y, {"x": X[0], "y": y[:, 0], "F": F, "F_max": F_max}
+        return super()._step(f, update_model)
+
     def F(self) -> torch.Tensor:
         """:20-25 — undirected if the safe set is (scalar-wise) inside the ROI."""
         roi = self.roi
         if self.model.safe_set_is_subset_of(A=roi):
             return _undirected(model=self.model)
-        inc = self.conditioning == "incremental" or (self.conditioning == "auto" and roi.fixed)
-        return _directed(model=self.model, roi=roi, incremental=inc)
+        return _directed(model=self.model, roi=roi, incremental=self._incremental(roi))
 
 
 def _undirected(model: MarginalModel) -> torch.Tensor:

@@ -15,11 +15,13 @@ from talgp.engine import DeviceGP
 
 
 def prior_distr(noise_rate, domain, X, y, kernels, means,
-                dtype: torch.dtype = torch.float64, comm=None, storage: str = "full") -> List[GaussianDistribution]:
+                dtype: torch.dtype = torch.float64, comm=None, storage: str = "full",
+                arith=None) -> List[GaussianDistribution]:
     """lib/gp/prior.py:34-66.  comm: a talgp.dist communicator to row-shard the
     covariances over the ranks (every rank calls this with the same arguments).
     storage: "full" (reference layout) or "lower" (only the blocks on or below the
-    diagonal are maintained; talgp.engine.DeviceGP)."""
+    diagonal are maintained; talgp.engine.DeviceGP).  arith: "two_rounding" (default) or "fma",
+    the arithmetic of the covariance update (talgp.engine.DeviceGP)."""
     domain = as_f64(domain)
     X = as_f64(X).reshape(-1, domain.shape[1])
     y = as_f64(y)
@@ -27,7 +29,7 @@ def prior_distr(noise_rate, domain, X, y, kernels, means,
     indices = get_indices(domain, X) if X.shape[0] > 0 else torch.zeros(
         (0,), dtype=torch.int64, device=domain.device)
     noise_rates = noise_rate.at(X)
-    gp = DeviceGP(domain.shape[0], q, dtype=dtype, device=domain.device, comm=comm, storage=storage)
+    gp = DeviceGP(domain.shape[0], q, dtype=dtype, device=domain.device, comm=comm, storage=storage, arith=arith)
     out = []
     for i in range(q):
         variance, lengthscale = kernels[i]._gram_params()

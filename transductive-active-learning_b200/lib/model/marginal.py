@@ -328,21 +328,39 @@ class MarginalModel(Model):
         return self.thompson_masks_from_samples(self._ts_samples(k), I, J)[1]
 
     # -- arg-max ---------------------------------------------------------------
-    def _argmax_index(self, F: torch.Tensor, sample_mask: Optional[torch.Tensor] = None):
-        """Masked arg-max kernel + the reference's three error checks
-        (:336-342).  F is overwritten with the sample-region-masked objective."""
-        safe = None
+    def _safe_override(self) -> Optional[torch.Tensor]:
+        """The operating safe set as a mask when a subclass overrides it (unsafe.py:9-13,
+        safe_opt/model.py:34-37); None = the pessimistic safe set, fused into the arg-max."""
         if type(self).operating_safe_set is not MarginalModel.operating_safe_set:
-            safe = self.operating_safe_set.view(torch.uint8)
-        gp = self._gp
-        if gp.sharded and F.numel() == self.n:  # a full-length objective: this rank's candidates
-            F = F[gp.cand0: gp.cand0 + gp.n_cand]
-        res = gp.read_result(gp.argmax_candidates(F, safe, self.first_constraint, sample_mask))
+            return self.operating_safe_set.view(torch.uint8)
+        return None
+
+    def _check_argmax(self, res) -> int:
+        """The reference's three error checks (:336-342) on an arg-max record."""
         self.last_argmax = res
         if res.status != _abi.ARGMAX_OK:
             raise Exception(_MESSAGES[res.status])
         self.acquire_key()  # the reference consumes one key per call (:346)
         return int(res.idx)
+
+    def _step_index(self, idx_dev: torch.Tensor, y, auto_select: bool = False) -> None:
+        """`step` for one observation at a domain index already on the device (:350-368)."""
+        beta = self._beta_now()  # evaluated at the OLD t (:366-368)
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            yv = y.reshape(-1)[: self.q] if y.numel() == self.q else y[:, 0].contiguous()
+        else:  # host observation: staged through the engine's pinned buffer, asynchronous H2D
+            yv = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y, dtype=np.float64).reshape(self.q, -1)[:, 0]
+        self._gp.observe(idx_dev, yv, beta, auto_select=auto_select)
+        self._t += 1
+
+    def _argmax_index(self, F: torch.Tensor, sample_mask: Optional[torch.Tensor] = None):
+        """Masked arg-max kernel + the reference's three error checks
+        (:336-342).  F is overwritten with the sample-region-masked objective."""
+        safe = self._safe_override()
+        gp = self._gp
+        if gp.sharded and F.numel() == self.n:  # a full-length objective: this rank's candidates
+            F = F[gp.cand0: gp.cand0 + gp.n_cand]
+        return self._check_argmax(gp.read_result(gp.argmax_candidates(F, safe, self.first_constraint, sample_mask)))
 
     def objective_argmax(self, F) -> torch.Tensor:
         """:330-348 — safe point maximising F (lowest index among exact ties)."""
@@ -356,13 +374,9 @@ class MarginalModel(Model):
         m = X.shape[0]
         beta = self._beta_now()  # evaluated at the OLD t (:366-368)
         if m == 1:
-            X_idx = self.get_indices(X)  # device int64[1]
-            if isinstance(y, torch.Tensor) and y.is_cuda:
-                yv = y.reshape(-1)[: self.q] if y.numel() == self.q else y[:, 0].contiguous()
-            else:  # host observation: staged through the engine's pinned buffer, asynchronous H2D
-                yv = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y, dtype=np.float64).reshape(self.q, -1)[:, 0]
-            self._gp.observe(X_idx, yv, beta)
-        elif m > 1:
+            self._step_index(self.get_indices(X), y)  # device int64[1]
+            return
+        if m > 1:
             X_idx = self.get_indices(X)
             noise_rate = self.noise_rate.at(X)
             y = as_f64(y)

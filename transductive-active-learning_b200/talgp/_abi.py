@@ -21,7 +21,8 @@ TAL_PEER_HANDLE_BYTES = 64
 F64, F32 = 0, 1
 KERNEL_GAUSSIAN, KERNEL_LAPLACE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(5)
 RULE_VTL, RULE_CTL, RULE_MMITL, RULE_TRUVAR = range(4)
-ARGMAX_OK, ARGMAX_EMPTY_SAFE_SET, ARGMAX_ALL_NEG_INF, ARGMAX_ALL_NAN = 0, 2, 3, 4
+ARGMAX_OK, ARGMAX_EMPTY_SAFE_SET, ARGMAX_ALL_NEG_INF, ARGMAX_ALL_NAN, ARGMAX_PEER_ERROR = 0, 2, 3, 4, 7
+ARITH_FMA = 16
 
 
 class ArgmaxResult(C.Structure):
@@ -56,6 +57,9 @@ class StepCtx(C.Structure):
         + [("bounds", C.c_longlong * 17)]
         + [("kbuf_off", C.c_longlong), ("pcol_off", C.c_longlong), ("pcol_peer", C.c_void_p), ("pcol_stride", C.c_longlong)]
         + [("ev_start", C.c_void_p * 64), ("ev_stop", C.c_void_p * 64), ("n_ev", C.c_longlong), ("timing", C.c_longlong)]
+        + [("ev_updates", C.c_longlong * 64)]
+        + [(n, C.c_longlong) for n in ("arith", "auto_select", "sel_state", "scal_ok")]
+        + [("sel_safe", C.c_void_p), ("sel_sample", C.c_void_p), ("sel_fc", C.c_longlong), ("fz_scratch", C.c_void_p)]
     )
 
 
@@ -127,7 +131,7 @@ SIGNATURES = {
     "tal_peer_publish_record": (_i, [_p, _p, _i, _i, _p]),
     "tal_peer_combine_records": (_i, [_p, _i, _p, _p]),
     "tal_peer_push_row": (_i, [_p, _i, _i, C.POINTER(_ll), _p, _ll, _ll, _ll, _i, _i, _p, _ll, _ll, _p, _ll,
-                               _ll, _ll, _ll, _ll, _ll, _i, _p]),
+                               _ll, _ll, _ll, _ll, _ll, _ll, _i, _p]),
     "tal_peer_wait_row": (_i, [_p, _i, _p, _ll, _p, _ll, _i, _p, _p]),
     "tal_sym_block": (_ll, [_i]),
     "tal_rankb_update": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _p, _ll, _i, _i, _i, _p]),
@@ -144,7 +148,9 @@ SIGNATURES = {
     "tal_ctx_step": (_i, [_p, _p]),
     "tal_ctx_flush": (_i, [_p, _p]),
     "tal_ctx_timing_begin": (_i, [_p]),
-    "tal_ctx_timing_read": (_i, [_p, C.POINTER(_d), C.POINTER(_ll), _p]),
+    "tal_ctx_timing_read": (_i, [_p, C.POINTER(_d), C.POINTER(_ll), C.POINTER(_ll), _p]),
+    "tal_ctx_observe_y": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
+    "tal_fused_scratch_bytes": (_ll, [_i, _ll, _i]),
     "tal_probe_fp64": (_i, [_i, _i, _i, _p, _p]),
 }
 

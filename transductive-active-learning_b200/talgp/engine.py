@@ -61,7 +61,7 @@ class DeviceGP:
     def __init__(self, N: int, q: int, dtype: torch.dtype = torch.float64,
                  device: Optional[torch.device] = None, row0: int = 0,
                  n_loc: Optional[int] = None, rank1_variant: int = 0, comm=None,
-                 storage: str = "full"):
+                 storage: str = "full", arith: Optional[str] = None):
         """comm: None (one GPU) or a communicator of talgp.dist (NcclComm /
         ThreadComm): the covariance is then row-sharded over comm.world ranks and
         this object holds rank comm.rank's block.
@@ -69,7 +69,11 @@ class DeviceGP:
         "lower" maintains only the blocks on or below the diagonal (the matrix is
         symmetric), which halves the HBM traffic of every posterior update; readers
         of full rows are served through the mirrored entries (include/tal_b200.h,
-        "lower-block storage")."""
+        "lower-block storage").
+        arith: "two_rounding" (default; c - rn(k w), bit-compatible with NumPy / an unfused
+        dot + subtract) or "fma" (one fused multiply-subtract per entry and update: half the
+        fp64 issue slots of the deferred pass); env TAL_UPDATE_ARITH.  The matrix, the pending
+        rows and `var` always share the mode, so var == diag(cov) holds bit for bit in both."""
         _abi.require_device()
         if storage not in ("full", "lower"):
             raise ValueError("storage must be 'full' or 'lower'")
@@ -89,6 +93,11 @@ class DeviceGP:
             raise ValueError("dtype must be torch.float64 or torch.float32")
         self.N, self.q = int(N), int(q)
         self.dtype, self.dt = dtype, _DT[dtype]
+        arith = arith or os.environ.get("TAL_UPDATE_ARITH", "two_rounding")
+        if arith not in ("two_rounding", "fma"):
+            raise ValueError("arith must be 'two_rounding' or 'fma'")
+        self.arith = arith
+        self.dt_upd = self.dt | (_abi.ARITH_FMA if arith == "fma" else 0)  # dtype argument of the update calls
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device())
         self.row0 = int(row0)
@@ -131,6 +140,8 @@ class DeviceGP:
         self._y_slot, self._y_event = 0, None
         self._ws = {}  # named scratch tensors, grown on demand
         self._cond = None  # incremental conditioning state (score_itl_directed)
+        self._ctx = None   # tal_step_ctx of the fused step (built on demand)
+        self.fused = os.environ.get("TAL_FUSED", "1") != "0"  # False: the kernel-by-kernel Python sequence
         self.cond_chunks = 0  # tal_cond_update: 0 = choose, 1 = single pass, > 1 = row-parallel
         # incremental conditioning: "append" (read-only pass + two appended rows per observation,
         # csrc/condapp.cu) or "downdate" (rewrites V every step, csrc/condinc.cu)
@@ -178,7 +189,7 @@ class DeviceGP:
             return False
         _abi.check(self.lib.tal_rankb_update(
             _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
-            _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld, p, int(self.lower), self.dt, _stream()),
+            _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld, p, int(self.lower), self.dt_upd, _stream()),
             "tal_rankb_update")
         self._Kp.zero_()
         self._Wp.zero_()
@@ -191,6 +202,8 @@ class DeviceGP:
         """(Re)allocate the peer mailboxes; the observed-row buffer kbuf and the
         conditioning column then live inside this rank's mailbox, where the
         owner of the row stores them (csrc/peer.cu).  Collective."""
+        self._sel_discard()
+        self._ctx = None  # (its cached mailbox pointers are about to be freed)
         self._peer = self.comm.attach(self.q, self.ld, self.dtype, int(m_pad), self.device)
         self.kbuf = self._peer.kbuf
         self._bounds_c = (C.c_longlong * len(self.bounds))(*self.bounds)
@@ -212,7 +225,8 @@ class DeviceGP:
             self.ld, self.N, self.q, int(self.lower), _ptr(idx_dev), int(idx_host), pv.kbuf_off,
             _ptr(st["V"]) if st is not None else None,
             st["cap"] * st["ncols"] if st is not None else 0, st["ncols"] if st is not None else 0,
-            st["rows"] if st is not None else 0, pv.pcol_off, self.cand0, self.n_cand, self.dt, _stream()),
+            st["rows"] if st is not None else 0, pv.pcol_off, pv.pcol.shape[1], self.cand0, self.n_cand,
+            self.dt, _stream()),
             "tal_peer_push_row")
         _abi.check(self.lib.tal_peer_wait_row(comm.box_ptr, comm.world, _ptr(idx_dev), int(idx_host), _ptr(self.mean),
                                               self.N, self.q, _ptr(self.scal), _stream()), "tal_peer_wait_row")
@@ -220,23 +234,28 @@ class DeviceGP:
 
     # ------------------------------------------------- one step as one host call
     def _ctx_usable(self) -> bool:
-        """The C-side step sequence (csrc/stepctx.cu) covers one GPU and the peer-memory sharded
-        model, with no conditioning state or the append form."""
-        if self.comm is not None and self._peer is None:
+        """The C-side step sequence (csrc/stepctx.cu + fused.cu) covers one GPU and the peer-memory
+        sharded model, with no conditioning state or the append form."""
+        if not self.fused or (self.comm is not None and self._peer is None):
             return False
         st = self._cond
         return st is None or st["append"]
 
     def _ctx_get(self) -> "_abi.StepCtx":
         st = self._cond
-        key = (None if st is None else st["V"].data_ptr(), None if st is None else st["cap"],
-               None if self._peer is None else self._peer.kbuf.data_ptr(), self.update_block,
-               self._Kp.data_ptr() if self.update_block > 1 else 0, self._cov.data_ptr())
+        F = self._scratch("ctx_F", (max(self.n_cand, 1),))
+        key = (None if st is None else (st["V"].data_ptr(), st["cap"], st["cs"].data_ptr(), st["fz"].data_ptr()),
+               None if self._peer is None else (self._peer.kbuf.data_ptr(), self.comm._table.data_ptr()),
+               self.update_block, self._Kp.data_ptr() if self.update_block > 1 else 0, self._cov.data_ptr(),
+               F.data_ptr(), self.arith)
         c = getattr(self, "_ctx", None)
         if c is None or self._ctx_key != key:
+            if c is not None:
+                self._sel_discard()  # (a published selection belongs to the old context)
             c = _abi.StepCtx()
             c.cov, c.cov_stride_q, c.ld, c.row0, c.n_loc = self._cov.data_ptr(), self.cov_stride_q, self.ld, self.row0, self.n_loc
             c.N, c.q, c.dtype, c.lower = self.N, self.q, self.dt, int(self.lower)
+            c.arith = int(self.arith == "fma")
             for name in ("mean", "var", "l", "u", "rho", "scal", "kbuf", "wbuf"):
                 setattr(c, name, getattr(self, name).data_ptr())
             if self.update_block > 1:
@@ -247,6 +266,8 @@ class DeviceGP:
             if st is not None:
                 c.Wb, c.ldw, c.cap_rows, c.m_pad, c.ncols = st["V"].data_ptr(), st["ncols"], st["cap"], st["m_pad"], st["ncols"]
                 c.n_split, c.cs, c.app_scratch, c.pcol = st["n_split"], st["cs"].data_ptr(), st["app"].data_ptr(), st["pcol"].data_ptr()
+                c.fz_scratch = st["fz"].data_ptr()
+            c.F = F.data_ptr()
             c.argmax_scratch = self._argmax_scratch.data_ptr()
             c.rec, c.combined = self._result.data_ptr(), self._result.data_ptr()
             c.G, c.rank = 1, 0
@@ -271,48 +292,80 @@ class DeviceGP:
         self._pending = int(c.pending)
         if self._cond is not None:
             self._cond["rows"] = int(c.rows)
+            if not c.cond_valid:
+                self._cond["valid"] = False
         if self.lower and c.passes:
             self._upper_stale = True
 
-    def ctx_observe(self, idx_dev, idx_host, y_dev: torch.Tensor, y_stride: int, y_gather: bool,
-                    beta: Sequence[float]) -> None:
-        """`observe` through tal_ctx_observe: the whole per-observation launch sequence in one call."""
+    def _sel_discard(self) -> None:
+        """The model is about to change outside the fused step: a selection that the previous
+        step made ahead of time is stale.  Sharded: its record was already published to the
+        peers, so the exchange is consumed (every rank does the same)."""
+        c = getattr(self, "_ctx", None)
+        if c is None or c.sel_state == 0:
+            return
+        if c.sel_state == 1:
+            _abi.check(self.lib.tal_peer_combine_records(self.comm.box_ptr, self.comm.world, _ptr(self._combined),
+                                                         _stream()), "tal_peer_combine_records")
+        c.sel_state, c.scal_ok = 0, 0
+
+    def _ctx_masks(self, c, first_constraint: int, safe, sample) -> None:
+        c.safe = safe.data_ptr() if safe is not None else None
+        c.sample = sample.data_ptr() if sample is not None else None
+        c.first_constraint = int(first_constraint)
+        self._ctx_mask_refs = (safe, sample)  # keep the tensors alive while the context points at them
+
+    def ctx_observe(self, idx_dev, idx_host, y_dev, y_stride: int, y_gather: bool,
+                    beta: Sequence[float], auto_select: bool = False) -> None:
+        """`observe` through tal_ctx_observe: the whole per-observation launch sequence in one call.
+        y_dev None: the value is supplied later with `ctx_observe_y`."""
         c = self._ctx_get()
         for i in range(self.q):
             c.beta[i] = float(beta[i])
+        c.auto_select = int(bool(auto_select))
         rc = self.lib.tal_ctx_observe(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
                                       int(bool(y_gather)), _stream())
-        if rc == _abi.TAL_CTX_REBASE:  # conditioning factor full: re-condition at the next scoring pass
-            self._cond["valid"] = False
-            c.cond_valid = 0
-            rc = self.lib.tal_ctx_observe(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
-                                          int(bool(y_gather)), _stream())
-        _abi.check(rc, "tal_ctx_observe")
+        if rc != _abi.TAL_CTX_REBASE:  # (REBASE: applied without the conditioning update, state marked stale)
+            _abi.check(rc, "tal_ctx_observe")
         self._ctx_done(c)
+
+    def ctx_observe_y(self, idx_dev, idx_host, y_dev: torch.Tensor, y_stride: int, y_gather: bool) -> None:
+        c = self._ctx
+        _abi.check(self.lib.tal_ctx_observe_y(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
+                                              int(bool(y_gather)), _stream()), "tal_ctx_observe_y")
+
+    def ctx_select(self, first_constraint: int, safe: Optional[torch.Tensor] = None,
+                   sample: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Directed-ITL selection over the resident conditioning state (nothing is launched when the
+        previous fused step already made it); returns the device record."""
+        st = self._cond
+        if not (self._ctx_usable() and st is not None and st["valid"]):
+            raise _abi.TalError("ctx_select needs a valid resident conditioning state (score_itl_directed(incremental=True))")
+        c = self._ctx_get()
+        self._ctx_masks(c, first_constraint, safe, sample)
+        _abi.check(self.lib.tal_ctx_select(C.byref(c), _stream()), "tal_ctx_select")
+        return self.argmax_record()
 
     def ctx_step(self, y_table: torch.Tensor, y_stride: int, beta: Sequence[float], first_constraint: int,
                  safe: Optional[torch.Tensor] = None, sample: Optional[torch.Tensor] = None) -> bool:
         """One greedy step of directed ITL over the resident conditioning state in one host call
-        (score -> masked arg-max -> exchange -> update); returns whether a pass over the matrix was
-        launched.  The selection is left in `argmax_record()`."""
+        (select -> exchange -> update -> selection of the next candidate); returns whether a pass
+        over the matrix was launched.  The selection is left in `argmax_record()`.  When the
+        conditioning factor is full the observation is applied without it and the state marked
+        stale: the caller's next scoring pass re-conditions from scratch."""
         st = self._cond
         if not (self._ctx_usable() and st is not None and st["valid"]):
             raise _abi.TalError("ctx_step needs a valid resident conditioning state (score_itl_directed(incremental=True))")
         c = self._ctx_get()
-        F = self._scratch("ctx_F", (max(self.n_cand, 1),))
-        c.F, c.safe, c.sample = F.data_ptr(), (safe.data_ptr() if safe is not None else None), (
-            sample.data_ptr() if sample is not None else None)
-        c.first_constraint = int(first_constraint)
+        self._ctx_masks(c, first_constraint, safe, sample)
         c.y_table, c.y_stride = y_table.data_ptr(), int(y_stride)
         for i in range(self.q):
             c.beta[i] = float(beta[i])
+        c.auto_select = 1
         passes = int(c.passes)
         rc = self.lib.tal_ctx_step(C.byref(c), _stream())
-        if rc == _abi.TAL_CTX_REBASE:
-            st["valid"] = False
-            self._ctx_done(c)
-            return False
-        _abi.check(rc, "tal_ctx_step")
+        if rc != _abi.TAL_CTX_REBASE:
+            _abi.check(rc, "tal_ctx_step")
         self._ctx_done(c)
         return int(c.passes) > passes
 
@@ -326,7 +379,7 @@ class DeviceGP:
             return
         _abi.check(self.lib.tal_pending_correct_row(
             _ptr(self.kbuf), self.ld, self.N, self.q, _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld,
-            self._pending, _ptr(idx_dev), int(idx_host), int(self.lower), self.dt, _stream()),
+            self._pending, _ptr(idx_dev), int(idx_host), int(self.lower), self.dt_upd, _stream()),
             "tal_pending_correct_row")
 
     def _sum(self, buf: torch.Tensor) -> None:
@@ -464,7 +517,7 @@ class DeviceGP:
         _abi.check(self.lib.tal_step_vectors(
             _ptr(self.kbuf), _ptr(self.wbuf), self.N, self.q, _ptr(idx_dev), int(idx_host),
             _ptr(y_dev), int(y_stride), int(bool(y_gather)), _ptr(self.rho), b, _ptr(self.scal),
-            _ptr(self.mean), _ptr(self.var), _ptr(self.l), _ptr(self.u), self.dt, _stream()),
+            _ptr(self.mean), _ptr(self.var), _ptr(self.l), _ptr(self.u), self.dt_upd, _stream()),
             "tal_step_vectors")
 
     def rank1_update(self, variant: Optional[int] = None) -> bool:
@@ -485,15 +538,15 @@ class DeviceGP:
             self._upper_stale = True
             _abi.check(self.lib.tal_rank1_update_lower(
                 _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
-                _ptr(self.kbuf), _ptr(self.wbuf), self.dt, _stream()), "tal_rank1_update_lower")
+                _ptr(self.kbuf), _ptr(self.wbuf), self.dt_upd, _stream()), "tal_rank1_update_lower")
             return
         _abi.check(self.lib.tal_rank1_update(
             _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
-            _ptr(self.kbuf), _ptr(self.wbuf), self.dt,
+            _ptr(self.kbuf), _ptr(self.wbuf), self.dt_upd,
             self.rank1_variant if variant is None else variant, _stream()), "tal_rank1_update")
 
     def observe(self, idx, y, beta: Sequence[float], y_gather: bool = False,
-                y_stride: int = 1, allreduce=None) -> None:
+                y_stride: int = 1, allreduce=None, auto_select: bool = False) -> None:
         """One observation at domain index `idx` (python int or 1-element int64
         device tensor) with values y[q] (host sequence, or device tensor; with
         y_gather a device table [q, y_stride] indexed at idx).
@@ -515,8 +568,9 @@ class DeviceGP:
                 self._y_event = torch.cuda.Event()
             self._y_event.record()
         if allreduce is None and self._ctx_usable():
-            self.ctx_observe(idx_dev, idx_host, y_dev, y_stride, y_gather, beta)
+            self.ctx_observe(idx_dev, idx_host, y_dev, y_stride, y_gather, beta, auto_select=auto_select)
             return
+        self._sel_discard()
         if allreduce is not None:
             self.extract_row(idx_dev, idx_host, correct=False)
             allreduce(self.kbuf)
@@ -537,6 +591,7 @@ class DeviceGP:
         m_total = int(obs_idx.numel())
         if m_total == 0:  # :23-24 short-circuit
             return
+        self._sel_discard()
         self.flush()
         if self._cond is not None:
             self._cond["valid"] = False  # general-m update: re-condition from scratch next time
@@ -783,6 +838,8 @@ class DeviceGP:
         F = torch.empty((n_out,), dtype=torch.float64, device=self.device)
         st = self._cond
         reuse = incremental and st is not None and st["key"] is roi_key and st["valid"]
+        if not reuse:
+            self._sel_discard()
         if incremental and not reuse:
             m_pad, ncols = self._cond_dims(m)
             append = self.cond_form == "append"
@@ -797,6 +854,8 @@ class DeviceGP:
                     st["n_split"] = int(max(1, min(64, m_pad // 64, -(-1184 // blocks))))
                     st["app"] = torch.empty((int(self.lib.tal_cond_append_scratch_bytes(ncols, st["n_split"])) // 8,),
                                             **f64)
+                    st["fz"] = torch.zeros((int(self.lib.tal_fused_scratch_bytes(self.q, ncols, st["n_split"])),),
+                                           dtype=torch.uint8, device=self.device)
                 else:
                     st["coef"] = torch.empty((int(self.lib.tal_cond_coef_bytes(m_pad)) // 8,), **f64)
                     st["chunk"] = torch.empty((int(self.lib.tal_cond_chunk_scratch_bytes(ncols)) // 8,), **f64)
@@ -855,7 +914,9 @@ class DeviceGP:
             st["rows"] = rows + 2
 
     def drop_conditioning(self) -> None:
+        self._sel_discard()
         self._cond = None
+        self._ctx = None  # (its cached pointers into the conditioning buffers are gone)
 
     # ------------------------------------------------------------------ argmax
     def masked_argmax(self, F: torch.Tensor, safe: Optional[torch.Tensor], first_constraint: int,
@@ -889,6 +950,7 @@ class DeviceGP:
         """_combined <- lexicographic reduce of every shard's arg-max record."""
         comm = self.comm
         if self._peer is not None:
+            self._sel_discard()  # (a record published ahead of time by the fused step is consumed first)
             _abi.check(self.lib.tal_peer_publish_record(_ptr(rec), comm.table_ptr, comm.world, comm.rank,
                                                         _stream()), "tal_peer_publish_record")
             _abi.check(self.lib.tal_peer_combine_records(comm.box_ptr, comm.world, _ptr(self._combined),
@@ -903,4 +965,8 @@ class DeviceGP:
         r = self._result if result is None else result
         self._result_host.copy_(r, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return _abi.ArgmaxResult.from_buffer_copy(self._result_host.numpy().tobytes())
+        res = _abi.ArgmaxResult.from_buffer_copy(self._result_host.numpy().tobytes())
+        if res.status == _abi.ARGMAX_PEER_ERROR or (self._peer is not None and res.flags & 8):
+            raise _abi.TalError(f"NVLink peer exchange timed out (TAL_PEER_ERR {self.comm.error()}): "
+                                "a rank is late or desynchronised; the replicated state is no longer trustworthy")
+        return res
