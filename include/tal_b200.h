@@ -177,8 +177,7 @@ int tal_sym_mirror(void* cov, long long cov_stride_q, long long ld, long long N,
 
 /* ---- temporally blocked posterior update ------------------------------------
  * The (k_i, w_i) of the last p <= TAL_MAX_PENDING observations may be kept pending
- * (K, W: [p][q][ld] of the cov dtype, `pend_stride` elements between slots, unused
- * slots zero) instead of streaming the matrix after every one of them:
+ * (K, W: [p][q][ld] of the cov dtype, `pend_stride` elements between slots) instead of streaming the matrix after every one of them:
  * tal_pending_correct_row applies them to the row that the next observation reads
  *   (kbuf [q][ld] as written by tal_extract_row[_lower] / the peer exchange):
  *   k[c] <- ((k[c] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ... with (a, b) = (idx, c), or

@@ -27,13 +27,18 @@ def child():
         pass
     variant = int(os.environ.get("TAL_RANKB_VARIANT", "0"))
     N = int(os.environ.get("MB_N", "65536"))
+    only_dt, only_ar, only_p = os.environ.get("MB_DTYPE"), os.environ.get("MB_ARITH"), os.environ.get("MB_P")
     for dtype in (torch.float64, torch.float32):
+        if only_dt and only_dt != ("f64" if dtype == torch.float64 else "f32"):
+            continue
         for arith in ("two_rounding", "fma"):
+            if only_ar and only_ar != arith:
+                continue
             gp = DeviceGP(N, 1, dtype=dtype, storage="lower", arith=arith)
             gp._cov.normal_()
             gp._Kp.normal_(); gp._Wp.normal_().mul_(1e-3)
             bytes_ = gp.update_bytes()
-            for p in (16, 8, 4):
+            for p in ((int(only_p),) if only_p else (16, 8, 4)):
                 def run():
                     _abi.check(gp.lib.tal_rankb_update(_ptr(gp._cov), gp.cov_stride_q, gp.ld, 0, N, N, 1, _ptr(gp._Kp),
                                                        _ptr(gp._Wp), gp.ld, p, 1, gp.dt_upd, _stream()))
@@ -60,6 +65,6 @@ if __name__ == "__main__":
         child()
     else:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        for v in (0, 1, 2, 3):
+        for v in (0, 1, 2, 3, 4):
             env = dict(os.environ, MB_CHILD="1", TAL_RANKB_VARIANT=str(v))
             subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)

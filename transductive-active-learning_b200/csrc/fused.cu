@@ -384,7 +384,7 @@ int fused_finish(const FusedFin& a, int dtype, cudaStream_t st) {
 extern "C" {
 
 long long tal_fused_scratch_bytes(int q, long long ncols, int n_split) {
-  return (long long)sizeof(tal::FusedScratch) + (long long)sizeof(double) * ((long long)q * n_split * (ncols + 1) + 8);
+  return (long long)sizeof(tal::FusedScratch) + (long long)sizeof(double) * ((long long)q * n_split * (ncols + 1) + 16);
 }
 
 }  // extern "C"

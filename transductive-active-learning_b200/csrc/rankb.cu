@@ -45,47 +45,57 @@ struct Lanes {
 };
 
 // grid: full storage (row blocks, column tiles, q); lower storage (column tiles, row blocks, q).
-// K, W: [P][q][ld] pending vectors (zero-padded beyond the p in use).  ROWS rows per CTA; the
-// CTA's K values are staged in shared memory ([P][ROWS]), every thread keeps its P w-vectors in
-// registers and has UNROLL rows of loads in flight.  PIPE: the loads of the next UNROLL rows are
-// issued before the arithmetic of the current ones (2 x UNROLL rows in flight per thread).
-template <typename T, int P, int UNROLL, bool FMA, bool PIPE>
+// K, W: [P][q][ld] pending vectors of which the first p are applied (slots >= p are not read).  One
+// CTA walks ROWS rows of a 256-vector column tile: its P w-vectors stay in registers for the whole
+// walk (they depend on the column only), the K values of its rows are staged in shared memory
+// ([P][ROWS]), UNROLL rows of loads are in flight per thread.  Lower storage: a thread starts at the
+// first row that keeps its column (the 32-row block that contains the column index).
+template <typename T, int P, int UNROLL, bool FMA, int ROWS>
 __global__ void __launch_bounds__(256, 2)
 rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, const T* __restrict__ K,
-             const T* __restrict__ W, i64 pend_stride, int rows_per_cta, i64 sym_block) {
+             const T* __restrict__ W, i64 pend_stride, int p, i64 sym_block) {
   typedef typename VecB<T>::type V;
   constexpr int VN = VecB<T>::n;
-  __shared__ T ksm[P][64];
+  __shared__ T ksm[P][ROWS];
   const int gp = blockIdx.z;
   const i64 rb = sym_block > 0 ? blockIdx.y : blockIdx.x;
   const i64 ct = sym_block > 0 ? blockIdx.x : blockIdx.y;
   const i64 col = (ct * 256 + threadIdx.x) * VN;
-  const i64 r0 = rb * rows_per_cta;
-  const i64 r1 = min(n_loc, r0 + (i64)rows_per_cta);
-  if (sym_block > 0 && ct * 256 * VN >= symb_cend(row0 + r0, sym_block, ld)) return;  // whole tile above
-  for (int e = threadIdx.x; e < P * rows_per_cta; e += 256) {
-    const int i = e / rows_per_cta, r = e % rows_per_cta;
-    ksm[i][r] = (r0 + r < r1) ? K[(i64)i * pend_stride + (i64)gp * ld + row0 + r0 + r] : T(0);
+  const i64 r0 = rb * ROWS;
+  const i64 r1 = min(n_loc, r0 + (i64)ROWS);
+  if (sym_block > 0 && ct * 256 * VN >= symb_cend(row0 + r1 - 1, sym_block, ld)) return;  // whole tile above
+  for (int e = threadIdx.x; e < P * ROWS; e += 256) {
+    const int i = e / ROWS, r = e % ROWS;
+    ksm[i][r] = (i < p && r0 + r < r1) ? K[(i64)i * pend_stride + (i64)gp * ld + row0 + r0 + r] : T(0);
   }
   __syncthreads();
   if (col >= ld) return;
-  if (sym_block > 0 && col >= symb_cend(row0 + r0, sym_block, ld)) return;
+  i64 rs = r0;
+  if (sym_block > 0) {
+    const i64 first = (col / sym_block) * sym_block - row0;  // rows before it keep this column in the mirror
+    if (first > rs) rs = first;
+  }
+  if (rs >= r1) return;
   Lanes<T, VN> wv[P];
 #pragma unroll
   for (int i = 0; i < P; ++i) {
-    const V t = *reinterpret_cast<const V*>(W + (i64)i * pend_stride + (i64)gp * ld + col);
-    memcpy(&wv[i], &t, sizeof(V));
+    if (i < p) {
+      const V t = *reinterpret_cast<const V*>(W + (i64)i * pend_stride + (i64)gp * ld + col);
+      memcpy(&wv[i], &t, sizeof(V));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) wv[i].v[e] = T(0);
+    }
   }
   T* C = cov + gp * stride_q + col;
-  auto load_rows = [&](Lanes<T, VN>* c, i64 r) {
+  for (i64 r = rs; r < r1; r += UNROLL) {
+    Lanes<T, VN> c[UNROLL];
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j)
       if (r + j < r1) {
         const V t = ld_stream(reinterpret_cast<const V*>(C + (r + j) * ld));
         memcpy(&c[j], &t, sizeof(V));
       }
-  };
-  auto update_rows = [&](Lanes<T, VN>* c, i64 r) {
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j)
       if (r + j < r1) {
@@ -99,22 +109,6 @@ rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, con
         memcpy(&t, &c[j], sizeof(V));
         st_stream(reinterpret_cast<V*>(C + (r + j) * ld), t);
       }
-  };
-  if constexpr (!PIPE) {
-    for (i64 r = r0; r < r1; r += UNROLL) {
-      Lanes<T, VN> c[UNROLL];
-      load_rows(c, r);
-      update_rows(c, r);
-    }
-  } else {
-    Lanes<T, VN> a[UNROLL], b[UNROLL];
-    load_rows(a, r0);
-    for (i64 r = r0; r < r1; r += 2 * UNROLL) {
-      load_rows(b, r + UNROLL);
-      update_rows(a, r);
-      load_rows(a, r + 2 * UNROLL);
-      update_rows(b, r + UNROLL);
-    }
   }
 }
 
@@ -140,8 +134,9 @@ pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict_
   kbuf[(i64)gp * ld + c] = v;
 }
 
-// Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = 0 (default: UNROLL 4 at P = 16, 8 below),
-// 1 (UNROLL 8 everywhere), 2 (software-pipelined, 2 x 4 rows in flight), 3 (pipelined, 2 x 2).
+// Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = 0 (default: 128 rows per CTA, UNROLL 4 at
+// P = 16 and 8 below), 1 (128 rows, UNROLL 8), 2 (256 rows, default UNROLL), 3 (256 rows, UNROLL 8),
+// 4 (32 rows per CTA: the round-1 shape).
 static int rankb_variant() {
   static int v = -1;
   if (v < 0) {
@@ -153,21 +148,23 @@ static int rankb_variant() {
 
 template <typename T, int P, bool FMA>
 static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
-                        i64 pend_stride, i64 sym_block, cudaStream_t st) {
+                        i64 pend_stride, int p, i64 sym_block, cudaStream_t st) {
   constexpr int VN = VecB<T>::n;
-  const int rows_per_cta = 32;
-  const unsigned row_blocks = (unsigned)((n_loc + rows_per_cta - 1) / rows_per_cta);
+  constexpr int UD = P >= 16 ? 4 : 8;  // P w-vectors + UNROLL rows in registers: 2 CTAs per SM
   const unsigned col_tiles = (unsigned)((ld + 256 * VN - 1) / (256 * VN));
-  dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);
-#define TAL_RB(U, PIPE)                                                                            \
-  rankb_kernel<T, P, U, FMA, PIPE><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, \
-                                                         rows_per_cta, sym_block)
+#define TAL_RB(U, ROWS)                                                                              \
+  do {                                                                                               \
+    const unsigned row_blocks = (unsigned)((n_loc + ROWS - 1) / ROWS);                               \
+    dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);     \
+    rankb_kernel<T, P, U, FMA, ROWS><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, p, \
+                                                           sym_block);                               \
+  } while (0)
   const int v = rankb_variant();
-  if (v == 1) TAL_RB(8, false);
-  else if (v == 2) TAL_RB(4, true);
-  else if (v == 3) TAL_RB(2, true);
-  else if (P >= 16) TAL_RB(4, false);  // P w-vectors + UNROLL rows in registers: 2 CTAs per SM
-  else TAL_RB(8, false);
+  if (v == 1) TAL_RB(8, 128);
+  else if (v == 2) TAL_RB(UD, 256);
+  else if (v == 3) TAL_RB(8, 256);
+  else if (v == 4) TAL_RB(UD, 32);
+  else TAL_RB(UD, 128);
 #undef TAL_RB
   return 0;
 }
@@ -175,10 +172,10 @@ static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
 template <typename T, bool FMA>
 static int rankb_dispatch(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q, const T* K, const T* W,
                           i64 pend_stride, int p, i64 sym_block, cudaStream_t st) {
-  if (p <= 2) return launch_rankb<T, 2, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  if (p <= 4) return launch_rankb<T, 4, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  if (p <= 8) return launch_rankb<T, 8, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
-  return launch_rankb<T, 16, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, sym_block, st);
+  if (p <= 2) return launch_rankb<T, 2, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
+  if (p <= 4) return launch_rankb<T, 4, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
+  if (p <= 8) return launch_rankb<T, 8, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
+  return launch_rankb<T, 16, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
 }
 
 }  // namespace tal
@@ -199,8 +196,6 @@ int tal_rankb_update(void* cov, long long cov_stride_q, long long ld, long long 
   TAL_ARG(row0 % 32 == 0);
   if (n_loc == 0) return TAL_OK;
   const i64 blk = lower ? tal_sym_block(dtype) : 0;
-  const unsigned row_blocks = (unsigned)((n_loc + 31) / 32);
-  if (lower) TAL_ARG(row_blocks <= 65535);
 #define TAL_RBD(T, F)                                                                             \
   rankb_dispatch<T, F>((T*)cov, cov_stride_q, ld, row0, n_loc, q, (const T*)K, (const T*)W, pend_stride, p, blk, \
                        as_stream(stream))

@@ -43,13 +43,7 @@ static int ctx_flush(tal_step_ctx* c, void* stream) {
                             c->pend_stride, (int)c->pending, (int)c->lower, upd_dtype(c), stream);
   ev_record(c, false, stream, c->pending);
   if (rc != TAL_OK) return rc;
-  // the pass is compiled for 2 / 4 / 8 / 16 slots and reads that many: the unused ones must be zero
-  // (a full block of `pend_slots` updates overwrites every slot, no clearing needed then)
-  if (c->pending != c->pend_slots) {
-    const size_t bytes = (size_t)c->pend_slots * (size_t)c->pend_stride * (c->dtype == TAL_F64 ? 8 : 4);
-    TAL_CUDA(cudaMemsetAsync(c->Kp, 0, bytes, as_stream(stream)));
-    TAL_CUDA(cudaMemsetAsync(c->Wp, 0, bytes, as_stream(stream)));
-  }
+  // (slots >= pending are never read: nothing to clear)
   c->pending = 0;
   c->passes += 1;
   return TAL_OK;
@@ -171,7 +165,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
   if (cond) {
     double* base = (double*)((char*)c->fz_scratch + sizeof(FusedScratch));
     double* colsq = base + 8;
-    double* part = colsq + (long long)q * c->n_split;
+    double* part = colsq + (((long long)q * c->n_split + 1) & ~1LL);  // (16-byte aligned: double2 stores)
     rc = fused_partial(c->Wb, c->cap_rows * c->ldw, c->ldw, c->rows, c->m_pad, idx_dev, idx_host, c->cand0, c->n_cand,
                        c->G > 1 ? c->pcol_peer : nullptr, c->pcol_stride, c->ncols, part, colsq, (int)c->n_split, q,
                        st);

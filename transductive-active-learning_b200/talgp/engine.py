@@ -173,8 +173,8 @@ class DeviceGP:
             self._alloc_pending()
 
     def _alloc_pending(self) -> None:
-        """Pending (k, w) slots: the pass is compiled for 2, 4, 8 or 16 of them and reads that many
-        (the unused ones are zero)."""
+        """Pending (k, w) slots (the pass is compiled for 2, 4, 8 or 16 of them; slots beyond the
+        number in use are not read)."""
         slots = 2
         while slots < self.update_block:
             slots *= 2
@@ -191,9 +191,7 @@ class DeviceGP:
             _ptr(self._cov), self.cov_stride_q, self.ld, self.row0, self.n_loc, self.N, self.q,
             _ptr(self._Kp), _ptr(self._Wp), self.q * self.ld, p, int(self.lower), self.dt_upd, _stream()),
             "tal_rankb_update")
-        self._Kp.zero_()
-        self._Wp.zero_()
-        self._pending = 0
+        self._pending = 0  # (slots >= p are never read: nothing to clear)
         if self.lower:
             self._upper_stale = True
         return True
