@@ -736,6 +736,8 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
             "invariants": {"state_finite__variances_positive__selection_in_pessimistic_safe_set": ok},
         }
         del model, alg, gp, distrs, f
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
     if rank != 0:
         return None
@@ -800,6 +802,8 @@ def run_ours(args, w):
     if rank == 0:
         line = dict(head, **body)
         line["clocks"] = {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]}
+    import gc
+    gc.collect()  # (model <-> ROI reference cycles keep the 34 GB matrix alive otherwise)
     torch.cuda.empty_cache()
 
     # ---- sub-records of the other named configs (same process, the c3 model is freed) -------------
@@ -815,6 +819,7 @@ def run_ours(args, w):
             c4 = {"error": repr(exc)[:300]}
         if rank == 0:
             line["c4"] = c4
+        gc.collect()
         torch.cuda.empty_cache()
         if world == 8:
             sub = argparse.Namespace(**vars(args))

@@ -75,7 +75,7 @@ extern "C" {
 
 /* result record written by tal_masked_argmax (32 bytes, device memory) */
 typedef struct tal_argmax_result {
-  long long idx;    /* lowest index among the exact ties at the maximum; -1 if none */
+  long long idx;    /* lowest index among the exact ties at the maximum; -1 if none or status != OK */
   double val;       /* nanmax of the safety-masked objective */
   long long n_ties; /* number of points attaining val exactly */
   int status;       /* TAL_ARGMAX_* (derived from flags) */

@@ -65,6 +65,6 @@ if __name__ == "__main__":
         child()
     else:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        for v in (0, 1, 2, 3, 4):
+        for v in [int(x) for x in os.environ.get("MB_VARIANTS", "0,1,2,3,4,5,6,7,8").split(",")]:
             env = dict(os.environ, MB_CHILD="1", TAL_RANKB_VARIANT=str(v))
             subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False)

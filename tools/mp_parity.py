@@ -91,7 +91,10 @@ def fused(storage, q, rank, world, dev, comm):
         for i in range(q):
             gp.build_gram(i, _abi.KERNEL_MATERN52 if i % 2 == 0 else _abi.KERNEL_GAUSSIAN, 1.0 + 0.5 * i,
                           0.3 + 0.1 * i, domain)
-        gp.rho.fill_(0.1); gp.init_bounds([2.0] * q)
+        gp.rho.fill_(0.1)
+        if q > 1:
+            gp.mean[1:].fill_(4.0)  # constraint GPs start pessimistically safe
+        gp.init_bounds([2.0] * q)
         return gp
 
     def run(gp):
@@ -101,10 +104,12 @@ def fused(storage, q, rank, world, dev, comm):
             if st is None or not st["valid"]:
                 F = gp.score_itl_directed(roi, m, incremental=True, roi_key=roi)
                 rec = gp.argmax_candidates(F, None, 1, None)
+                sel.append(int(rec[0].item()))
                 gp.observe(rec[0:1].clone(), table, [2.0] * q, y_gather=True, y_stride=N)
             else:
+                if t % 5 == 0:  # (reading it first takes the stand-alone combine path; otherwise the push combines)
+                    sel.append(int(gp.ctx_select(1, None, None)[0].item()))
                 gp.ctx_step(table, N, [2.0] * q, 1, None, None)
-            sel.append(int(gp.argmax_record()[0].item()))
         gp.flush()
         torch.cuda.synchronize()
         return sel

@@ -65,12 +65,15 @@ __device__ __forceinline__ int status_of(int flags) {
   return TAL_ARGMAX_OK;
 }
 
+// idx is -1 whenever the arg-max failed (status != OK): the update kernels treat a negative index
+// as "no observation", so a failed selection can never be applied by a device-resident loop.
 __device__ __forceinline__ void write_result(const Rec& r, tal_argmax_result* out) {
-  out->idx = r.cnt ? r.idx : -1;
+  const int status = status_of(r.flags);
+  out->idx = (r.cnt && status == TAL_ARGMAX_OK) ? r.idx : -1;
   out->val = r.val;
   out->n_ties = r.cnt;
   out->flags = r.flags;
-  out->status = status_of(r.flags);
+  out->status = status;
 }
 
 // per-candidate record of the masked objective (lib/algorithms/__init__.py:80, marginal.py:336-345)

@@ -93,14 +93,14 @@ __device__ __forceinline__ tal_argmax_result combine_records_warp(PeerHeader* h,
     }
   }
   tal_argmax_result out;
-  out.idx = cnt ? idx : -1;
-  out.val = val;
-  out.n_ties = cnt;
-  out.flags = flags;
   out.status = (flags & 8) ? TAL_ARGMAX_PEER_ERROR
                : !(flags & 1) ? TAL_ARGMAX_EMPTY_SAFE_SET
                : !(flags & 2) ? TAL_ARGMAX_ALL_NEG_INF
                : !(flags & 4) ? TAL_ARGMAX_ALL_NAN : TAL_ARGMAX_OK;
+  out.idx = (cnt && out.status == TAL_ARGMAX_OK) ? idx : -1;  // (a failed arg-max is never applied)
+  out.val = val;
+  out.n_ties = cnt;
+  out.flags = flags;
   return out;
 }
 

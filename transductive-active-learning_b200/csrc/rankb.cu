@@ -112,6 +112,94 @@ rankb_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, con
   }
 }
 
+// The same pass with the row loads decoupled from the registers: every thread streams ITS OWN 16-byte
+// column slice through a private ring of D shared-memory slots with cp.async (no barrier: a thread only
+// ever reads what it copied itself), so D rows per thread stay in flight while the fp64 chain of the
+// current row runs.  At P = 16 the register-resident variant above holds only 4 rows in flight next to
+// its 64 w-registers and is latency-bound (ncu: 62 % DRAM, 72 % of the cycles no warp eligible, long
+// scoreboard); here the bytes in flight per SM are D x 4 KB x 2 CTAs regardless of the arithmetic.
+__device__ __forceinline__ void rb_cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void rb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rb_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T, int P, bool FMA, int ROWS, int D>
+__global__ void __launch_bounds__(256, 2)
+rankb_async_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, const T* __restrict__ K,
+                   const T* __restrict__ W, i64 pend_stride, int p, i64 sym_block) {
+  typedef typename VecB<T>::type V;
+  constexpr int VN = VecB<T>::n;
+  extern __shared__ __align__(16) unsigned char rb_smem[];
+  V* ring = reinterpret_cast<V*>(rb_smem);                       // [D][256]
+  T (*ksm)[ROWS] = reinterpret_cast<T (*)[ROWS]>(rb_smem + (size_t)D * 256 * sizeof(V));  // [P][ROWS]
+  const int gp = blockIdx.z;
+  const i64 rb = sym_block > 0 ? blockIdx.y : blockIdx.x;
+  const i64 ct = sym_block > 0 ? blockIdx.x : blockIdx.y;
+  const i64 col = (ct * 256 + threadIdx.x) * VN;
+  const i64 r0 = rb * ROWS;
+  const i64 r1 = min(n_loc, r0 + (i64)ROWS);
+  if (sym_block > 0 && ct * 256 * VN >= symb_cend(row0 + r1 - 1, sym_block, ld)) return;  // whole tile above
+  i64 rs = r0;
+  if (sym_block > 0) {
+    const i64 first = (col / sym_block) * sym_block - row0;
+    if (first > rs) rs = first;
+  }
+  const bool active = col < ld && rs < r1;
+  T* C = cov + gp * stride_q + col;
+  V* mine = ring + threadIdx.x;
+  if (active) {  // the first D rows are on their way while K and W are fetched
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (rs + d < r1) rb_cp_async16(mine + d * 256, C + (rs + d) * ld);
+      rb_cp_async_commit();
+    }
+  }
+  for (int e = threadIdx.x; e < P * ROWS; e += 256) {
+    const int i = e / ROWS, r = e % ROWS;
+    ksm[i][r] = (i < p && r0 + r < r1) ? K[(i64)i * pend_stride + (i64)gp * ld + row0 + r0 + r] : T(0);
+  }
+  __syncthreads();
+  if (!active) return;
+  Lanes<T, VN> wv[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    if (i < p) {
+      const V t = *reinterpret_cast<const V*>(W + (i64)i * pend_stride + (i64)gp * ld + col);
+      memcpy(&wv[i], &t, sizeof(V));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) wv[i].v[e] = T(0);
+    }
+  }
+  int slot = 0;
+  for (i64 r = rs; r < r1; ++r) {
+    rb_cp_async_wait<D - 1>();  // this thread's copy of row r has landed
+    Lanes<T, VN> c;
+    {
+      const V t = mine[slot * 256];
+      memcpy(&c, &t, sizeof(V));
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const T kk = ksm[i][r - r0];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) c.v[e] = sub_prod_m<FMA>(c.v[e], kk, wv[i].v[e]);
+    }
+    V t;
+    memcpy(&t, &c, sizeof(V));
+    st_stream(reinterpret_cast<V*>(C + r * ld), t);
+    // the slot is free again (its value went through the arithmetic above): fetch row r + D into it
+    if (r + D < r1) rb_cp_async16(mine + slot * 256, C + (r + D) * ld);
+    rb_cp_async_commit();
+    slot = slot + 1 == D ? 0 : slot + 1;
+  }
+}
+
 // k[c] <- (((k[c] - K_0[a] W_0[b]) - K_1[a] W_1[b]) - ...) with (a, b) = (x, c) for the entries the row
 // x keeps and (c, x) for the mirrored ones (lower-block storage): exactly what the deferred passes
 // will do to those entries.  grid (ceil(ld / 256), q).
@@ -136,7 +224,8 @@ pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict_
 
 // Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = 0 (default: 128 rows per CTA, UNROLL 4 at
 // P = 16 and 8 below), 1 (128 rows, UNROLL 8), 2 (256 rows, default UNROLL), 3 (256 rows, UNROLL 8),
-// 4 (32 rows per CTA: the round-1 shape).
+// 4 (32 rows per CTA: the round-1 shape), 5 / 6 / 8 (cp.async ring of 8 / 16 / 24 rows per thread, 128 rows per
+// CTA), 7 (ring of 16, 256 rows per CTA).
 static int rankb_variant() {
   static int v = -1;
   if (v < 0) {
@@ -159,13 +248,32 @@ static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
     rankb_kernel<T, P, U, FMA, ROWS><<<grid, 256, 0, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, p, \
                                                            sym_block);                               \
   } while (0)
+#define TAL_RBA(ROWS, D)                                                                             \
+  do {                                                                                               \
+    typedef typename VecB<T>::type V_;                                                               \
+    const size_t smem = (size_t)D * 256 * sizeof(V_) + (size_t)P * ROWS * sizeof(T);                 \
+    auto kern = rankb_async_kernel<T, P, FMA, ROWS, D>;                                              \
+    static bool attr = false;                                                                        \
+    if (!attr) {                                                                                     \
+      TAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+      attr = true;                                                                                   \
+    }                                                                                                \
+    const unsigned row_blocks = (unsigned)((n_loc + ROWS - 1) / ROWS);                               \
+    dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);     \
+    kern<<<grid, 256, smem, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, p, sym_block);  \
+  } while (0)
   const int v = rankb_variant();
-  if (v == 1) TAL_RB(8, 128);
+  if (v == 5) TAL_RBA(128, 8);
+  else if (v == 6) TAL_RBA(128, 16);
+  else if (v == 7) TAL_RBA(256, 16);
+  else if (v == 8) TAL_RBA(128, 24);
+  else if (v == 1) TAL_RB(8, 128);
   else if (v == 2) TAL_RB(UD, 256);
   else if (v == 3) TAL_RB(8, 256);
   else if (v == 4) TAL_RB(UD, 32);
   else TAL_RB(UD, 128);
 #undef TAL_RB
+#undef TAL_RBA
   return 0;
 }
 
