@@ -333,8 +333,14 @@ def recompute_kernels(gp, roi_idx, m, hbm_peak):
     lib = gp.lib
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    big = m > 16384  # (C4 ITL-PM: seconds per call -- one timed call each, no dry run)
+
     def timed(fn, reps=3):
-        fn(); torch.cuda.synchronize()
+        if big:
+            reps = 1
+        else:
+            fn()
+        torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
             a, b = _events()
@@ -657,11 +663,18 @@ def run_itl(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, war
 
 
 # ---------------------------------------------------------------------- Safe-BO arm
-def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, warmup):
+def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, warmup, rules=("VTL-PM", "ITL-PM"),
+             itl_steps=2):
     """C4: batched Safe BO through the drop-in API (device-resident black box): every step computes the
     potential-maximiser ROI from the confidence bounds of the 5 GPs, scores all candidates (VTL-PM, then
     ITL-PM in a second model), takes the safe-set-masked arg-max (the pessimistic safe set is fused into
-    the arg-max kernel) and updates all 5 covariances."""
+    the arg-max kernel) and updates all 5 covariances.
+
+    ITL-PM: with 10 observations at the seed the potential maximisers are almost the whole domain
+    (m ~ N - 10), and the safe set is not inside them, so the reference's rule is the DIRECTED one
+    (lib/algorithms/itl.py:22-25): per step and GP a Cholesky of an m x m and a triangular solve of an
+    m x N matrix, m^3/3 + m^2 N = 3.8e14 fp64 flop at N = 65,536 (the reference: 2 N^2 m).  It is timed for
+    `itl_steps` steps without warm-up (every step re-conditions from scratch: there is nothing to warm)."""
     import torch
     import torch.distributed as dist
     from lib.algorithms import pm_roi_constructor
@@ -677,7 +690,9 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
     q, N = w["q"], w["N"]
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
     out = {}
-    for rule in ("VTL-PM", "ITL-PM"):
+    for rule in rules:
+        is_itl = rule == "ITL-PM"
+        steps_r, warmup_r = (max(1, min(steps, itl_steps)), 0) if (is_itl and N > 16384) else (steps, warmup)
         noise = HomoscedasticNoise(q, np.full(q, w["rho"]))
         distrs = prior_distr(noise, domain, domain[prior_idx], table[:, prior_idx],
                              [stationary.Matern52(lengthscale=l) for l in w["lengthscales"]], [ZeroMean()] * q,
@@ -688,7 +703,7 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
         alg.gather_F = False
         f = TableFunction(model.domain, table)
         ms_roi = []
-        for _ in range(warmup):
+        for _ in range(warmup_r):
             alg.step(f)
         gp.flush()
         torch.cuda.synchronize()
@@ -697,8 +712,8 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
         lib.tal_reset_launch_count()
         t0, t1 = _events()
         t0.record()
-        for _ in range(steps):
-            ms_roi.append(alg.roi.m if steps <= 64 else 0)
+        for _ in range(steps_r):
+            ms_roi.append(alg.roi.m if steps_r <= 64 else 0)
             alg.step(f)
         gp.flush()
         t1.record()
@@ -724,15 +739,22 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
         if world > 1 and getattr(gp.comm, "peer", False):
             assert gp.comm.error() == 0
         alg_bytes = gp.update_bytes()
+        kernels = []
+        if is_itl and world == 1 and alg.roi.m > 0:
+            try:
+                kernels = recompute_kernels(gp, alg.roi.idx, alg.roi.m, hbm_peak)
+            except Exception as exc:  # pragma: no cover
+                kernels = [{"error": repr(exc)[:200]}]
         out[rule] = {
-            "value": steps / (total_ms / 1e3), "unit": UNIT, "ms_per_step": total_ms / steps, "steps": steps,
-            "roi_size_per_step": ms_roi, "safe_set_size": int(pess.sum()), "gpu_launches": launches,
+            "kernels": kernels,
+            "value": steps_r / (total_ms / 1e3), "unit": UNIT, "ms_per_step": total_ms / steps_r, "steps": steps_r,
+            "warmup": warmup_r, "roi_size_per_step": ms_roi, "safe_set_size": int(pess.sum()), "gpu_launches": launches,
             "roofline": {"kernel": "rank1_update%s over the %d covariances (one pass per step: the scoring reads "
                                    "the matrix)" % ("_lower" if gp.lower else "", q),
                          "bound": "hbm", "achieved": alg_bytes / (upd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / (upd_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": upd_ms,
-                         "share_of_step": upd_ms / (total_ms / steps)},
+                         "share_of_step": upd_ms / (total_ms / steps_r)},
             "invariants": {"state_finite__variances_positive__selection_in_pessimistic_safe_set": ok},
         }
         del model, alg, gp, distrs, f
@@ -741,8 +763,9 @@ def run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, wa
         torch.cuda.empty_cache()
     if rank != 0:
         return None
+    first = out[rules[0]]
     return {"config": workload_config(args, w, world), "rules": out,
-            "value": out["VTL-PM"]["value"], "ms_per_step": out["VTL-PM"]["ms_per_step"],
+            "value": first["value"], "ms_per_step": first["ms_per_step"],
             "api": "lib.algorithms.{vtl.VTL, itl.ITL}(model, pm_roi_constructor).step(f), device-resident black box "
                    "(TableFunction); per step one D2H of the ROI size and one of the arg-max record"}
 
@@ -781,10 +804,11 @@ def run_ours(args, w):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic"}
     if w["kind"] == "safe":
-        body = run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, args.steps, args.warmup)
+        body = run_safe(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, args.steps, args.warmup,
+                        rules=tuple(args.rules.split(",")), itl_steps=args.itl_steps)
         clk = clocks.stop()
         if rank == 0:
-            r = body["rules"]["VTL-PM"]
+            r = list(body["rules"].values())[0]
             line = dict(head, **body)
             line["roofline"] = r["roofline"]
             line["gpu_launches"] = r["gpu_launches"]
@@ -813,8 +837,10 @@ def run_ours(args, w):
         if world == 1:
             sub.dtype = "f32"  # 5 x 34 GB in fp64 does not fit one GPU
         try:
+            # (ITL-PM at this size is 3.8e14 fp64 flop per GP and step -- tens of seconds: it has its own run,
+            # `bench.py --workload c4`, whose line is kept under profiles/)
             c4 = run_safe(sub, WORKLOADS["c4"], dev, world, rank, comm, lib, hbm_peak, peak_src,
-                          steps=min(args.steps, 16), warmup=2)
+                          steps=min(args.steps, 16), warmup=2, rules=("VTL-PM",))
         except Exception as exc:  # pragma: no cover
             c4 = {"error": repr(exc)[:300]}
         if rank == 0:
@@ -901,6 +927,8 @@ def main():
                     help="update arithmetic: one fused multiply-subtract per entry (fma) or product rounded first")
     ap.add_argument("--dtype", default=None, choices=["f64", "f32"],
                     help="covariance storage / arithmetic type (the reference's only mode is f64)")
+    ap.add_argument("--rules", default="VTL-PM,ITL-PM", help="c4: acquisition rules to time")
+    ap.add_argument("--itl-steps", type=int, default=2, help="c4 at full size: timed ITL-PM steps (tens of seconds each)")
     ap.add_argument("--cpu-sample-n", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-both", dest="both", action="store_false", help="skip the variant sub-runs")

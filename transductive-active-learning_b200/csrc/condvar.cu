@@ -25,9 +25,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gather_roi_B_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restrict__ roi_idx,
                     i64 m, double* __restrict__ B, i64 ldb) {
-  // grid.y over padded rows; pad rows / pad columns are zero
-  const i64 j = blockIdx.y;
-  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid.x over padded rows (up to N of them: the ROI can be the whole domain); pad rows / columns are zero
+  const i64 j = blockIdx.x;
+  const i64 col = (i64)blockIdx.y * blockDim.x + threadIdx.x;
   if (col >= ldb) return;
   double v = 0.0;
   if (j < m && col < N) v = (double)cov[roi_idx[j] * ld + col];
@@ -40,8 +40,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gather_roi_B_lower_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restrict__ roi_idx,
                           i64 m, double* __restrict__ B, i64 ldb, i64 sym_block) {
-  const i64 j = blockIdx.y;
-  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.x;
+  const i64 col = (i64)blockIdx.y * blockDim.x + threadIdx.x;
   if (col >= ldb) return;
   double v = 0.0;
   if (j < m && col < N) {
@@ -54,8 +54,8 @@ gather_roi_B_lower_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* _
 __global__ void __launch_bounds__(256)
 gather_roi_S_kernel(const double* __restrict__ B, i64 ldb, const i64* __restrict__ roi_idx, i64 m,
                     i64 m_pad, double jitter, double* __restrict__ S, i64 lds) {
-  const i64 j = blockIdx.y;
-  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.x;
+  const i64 k = (i64)blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= m_pad) return;
   double v;
   if (j < m && k < m) {
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(256)
 gather_roi_S_rows_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc,
                          const i64* __restrict__ roi_idx, i64 m, i64 m_pad, double jitter,
                          double* __restrict__ S, i64 lds) {
-  const i64 j = blockIdx.y;
-  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 j = blockIdx.x;
+  const i64 k = (i64)blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= m_pad) return;
   double v = 0.0;
   if (j < m && k < m) {
@@ -493,16 +493,16 @@ int tal_gather_roi(const void* cov, long long ld, long long N, const long long* 
                    long long m, long long m_pad, double jitter, double* S, long long lds,
                    double* B, long long ldb, int dtype, void* stream) {
   TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
-  TAL_ARG(lds >= m_pad && ldb >= N && m_pad <= 65535);
+  TAL_ARG(lds >= m_pad && ldb >= N && ldb <= 65535 * 256);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   cudaStream_t st = as_stream(stream);
-  dim3 gb((unsigned)((ldb + 255) / 256), (unsigned)m_pad);
+  dim3 gb((unsigned)m_pad, (unsigned)((ldb + 255) / 256));
   if (dtype == TAL_F64)
     gather_roi_B_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, N, roi_idx, m, B, ldb);
   else
     gather_roi_B_kernel<float><<<gb, 256, 0, st>>>((const float*)cov, ld, N, roi_idx, m, B, ldb);
   TAL_LAUNCH_CHECK("tal_gather_roi/B");
-  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  dim3 gs((unsigned)m_pad, (unsigned)((m_pad + 255) / 256));
   gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
   TAL_LAUNCH_CHECK("tal_gather_roi/S");
   return TAL_OK;
@@ -512,17 +512,17 @@ int tal_gather_roi_lower(const void* cov, long long ld, long long N, const long 
                          long long m, long long m_pad, double jitter, double* S, long long lds,
                          double* B, long long ldb, int dtype, void* stream) {
   TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
-  TAL_ARG(lds >= m_pad && ldb >= N && m_pad <= 65535);
+  TAL_ARG(lds >= m_pad && ldb >= N && ldb <= 65535 * 256);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   cudaStream_t st = as_stream(stream);
   const i64 blk = tal_sym_block(dtype);
-  dim3 gb((unsigned)((ldb + 255) / 256), (unsigned)m_pad);
+  dim3 gb((unsigned)m_pad, (unsigned)((ldb + 255) / 256));
   if (dtype == TAL_F64)
     gather_roi_B_lower_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, N, roi_idx, m, B, ldb, blk);
   else
     gather_roi_B_lower_kernel<float><<<gb, 256, 0, st>>>((const float*)cov, ld, N, roi_idx, m, B, ldb, blk);
   TAL_LAUNCH_CHECK("tal_gather_roi_lower/B");
-  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  dim3 gs((unsigned)m_pad, (unsigned)((m_pad + 255) / 256));
   gather_roi_S_kernel<<<gs, 256, 0, st>>>(B, ldb, roi_idx, m, m_pad, jitter, S, lds);
   TAL_LAUNCH_CHECK("tal_gather_roi_lower/S");
   return TAL_OK;
@@ -533,11 +533,11 @@ int tal_gather_roi_sharded(const void* cov, long long ld, long long row0, long l
                            double* S, long long lds, double* B, long long ldb, long long ncols,
                            int dtype, void* stream) {
   TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
-  TAL_ARG(lds >= m_pad && ldb >= ncols && ncols >= n_loc && m_pad <= 65535 && n_loc >= 0);
+  TAL_ARG(lds >= m_pad && ldb >= ncols && ncols >= n_loc && m_pad <= 65535 * 32 && n_loc >= 0);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   cudaStream_t st = as_stream(stream);
   dim3 gb((unsigned)((ncols + 31) / 32), (unsigned)(m_pad / 32));
-  dim3 gs((unsigned)((m_pad + 255) / 256), (unsigned)m_pad);
+  dim3 gs((unsigned)m_pad, (unsigned)((m_pad + 255) / 256));
   if (dtype == TAL_F64) {
     gather_roi_cols_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, n_loc, roi_idx, m, B, ldb, ncols);
     TAL_LAUNCH_CHECK("tal_gather_roi_sharded/B");

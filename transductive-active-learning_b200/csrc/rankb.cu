@@ -222,15 +222,18 @@ pending_correct_kernel(T* __restrict__ kbuf, i64 ld, i64 N, const T* __restrict_
   kbuf[(i64)gp * ld + c] = v;
 }
 
-// Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = 0 (default: 128 rows per CTA, UNROLL 4 at
-// P = 16 and 8 below), 1 (128 rows, UNROLL 8), 2 (256 rows, default UNROLL), 3 (256 rows, UNROLL 8),
-// 4 (32 rows per CTA: the round-1 shape), 5 / 6 / 8 (cp.async ring of 8 / 16 / 24 rows per thread, 128 rows per
-// CTA), 7 (ring of 16, 256 rows per CTA).
+// Tuning knob (microbenchmarks only): TAL_RANKB_VARIANT = -1 (default, chosen from the measurements in
+// profiles/r02_rankb_variants.md: the cp.async ring at P = 16, where the register-resident kernel is
+// latency-bound -- ring of 16 rows with FMA arithmetic, of 8 with two roundings -- and the register-resident
+// kernel with 128 rows per CTA below, which already runs at the copy roofline), 0 (register-resident, 128 rows
+// per CTA, UNROLL 4 at P = 16 and 8 below), 1 (128 rows, UNROLL 8), 2 (256 rows, default UNROLL), 3 (256 rows,
+// UNROLL 8), 4 (32 rows per CTA: the round-1 shape), 5 / 6 / 8 (cp.async ring of 8 / 16 / 24 rows per thread,
+// 128 rows per CTA), 7 (ring of 16, 256 rows per CTA).
 static int rankb_variant() {
-  static int v = -1;
-  if (v < 0) {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("TAL_RANKB_VARIANT");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : -1;
   }
   return v;
 }
@@ -262,7 +265,8 @@ static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
     dim3 grid = sym_block > 0 ? dim3(col_tiles, row_blocks, q) : dim3(row_blocks, col_tiles, q);     \
     kern<<<grid, 256, smem, st>>>(cov, stride_q, ld, row0, n_loc, K, W, pend_stride, p, sym_block);  \
   } while (0)
-  const int v = rankb_variant();
+  int v = rankb_variant();
+  if (v < 0) v = P >= 16 ? (FMA ? 6 : 5) : 0;
   if (v == 5) TAL_RBA(128, 8);
   else if (v == 6) TAL_RBA(128, 16);
   else if (v == 7) TAL_RBA(256, 16);
