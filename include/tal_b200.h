@@ -329,6 +329,38 @@ int tal_colsumsq_dense(const double* V, long long ldv, long long m, long long n_
 int tal_score_itl_directed(const double* var, const double* cs, const double* rho,
                            long long n, int accumulate, double* F, void* stream);
 
+/* ---- dense blocks of a covariance: sampling, entropy, information gain -----
+ * SURVEY.md 8f-4.  All of them are: gather a block, factor it with
+ * tal_potrf_lower (blocked DMMA Cholesky; the reference calls SVD / slogdet /
+ * cholesky of XLA:CPU), then one small pass over the factor.
+ * tal_gather_sym_block: S[j][k] = cov[idx[j]][idx[k]] + (j == k) (add + add_std[j]^2),
+ *   identity pad up to m_pad (idx == NULL: the leading m x m block; lower != 0:
+ *   lower-block storage, mirrored entries) — GaussianDistribution.sub_distr
+ *   (lib/gp/gaussian_distribution.py:182-187), MarginalModel.masked_distr, the
+ *   `covariance[ix_(obs, obs)] + noise_covariance_matrix` of .information_gain (:163-173)
+ *   and the `+ jitter * eye` of .entropy (:145-148).
+ * tal_chol_logdet: out[0] = 2 sum_{i<m} log L[i][i] = slogdet(S)[1] for the factored S
+ *   (:141-149, :174-177).
+ * tal_tri_sample: out[s][r] = mean[r] + sum_{c<=r} L[r][c] Z[s][c] for k draws Z[k][ldz]
+ *   (GaussianDistribution.sample :90-98, MarginalModel.sample lib/model/marginal.py:226-237:
+ *   the reference factors the covariance again for every draw).
+ * tal_gather_cols_t: Vt[i][j] = V[j][idx[i]] (i < nb; zero rows up to nb_pad) — the columns B of
+ *   V = L^-1 cov[A, :] transposed for the SYRK below.
+ * tal_syrk_lower_sub: C <- C - A A^T on the 128 x 128 tiles on or below the diagonal
+ *   (A is [n][K], n % 128 == 0, K % 16 == 0): the posterior block
+ *   Sigma_BB - Sigma_BA (Sigma_AA + jitter^2 I)^-1 Sigma_AB of .information_gain (:164-169)
+ *   as Sigma_BB - V_B^T V_B on the fp64 tensor path.                          */
+int tal_gather_sym_block(const void* cov, long long ld, long long N, const long long* idx, long long m,
+                         long long m_pad, const double* add_std, double add, double* S, long long lds,
+                         int lower, int dtype, void* stream);
+int tal_chol_logdet(const double* L, long long lds, long long m, double* out, void* stream);
+int tal_tri_sample(const double* L, long long lds, long long n, const double* Z, long long ldz, int k,
+                   const double* mean, double* out, long long ldo, void* stream);
+int tal_gather_cols_t(const double* V, long long ldv, long long m_pad, const long long* idx, long long nb,
+                      long long nb_pad, double* Vt, long long ldvt, void* stream);
+int tal_syrk_lower_sub(double* C, long long ldc, long long n, const double* A, long long lda, long long K,
+                       void* stream);
+
 /* ---- incremental conditioning for a fixed ROI ---------------------------
  * Beyond the reference (which re-runs the m x m Cholesky and the m x N solves
  * of lib/algorithms/itl.py:41-48 at every step): when the ROI is unchanged,

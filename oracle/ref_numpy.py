@@ -30,6 +30,8 @@ __all__ = [
     "LineBO",
     "UnknownFunction",
     "thompson_masks_from_samples",
+    "compute_strong_information_ratio",
+    "compute_information_ratio",
     "DEFAULT_JITTER",
     "solve_linear_system",
     "noise_covariance_matrix",
@@ -351,6 +353,28 @@ class GaussianDistribution:
         idx = np.asarray(idx, dtype=np.int64)
         return GaussianDistribution(mean=self.mean[idx], covariance=self.covariance[np.ix_(idx, idx)])
 
+    def entropy(self, jitter: float = 0.0):  # :141-149
+        return 0.5 * (
+            self.n * np.log(2 * np.pi * np.e)
+            + np.linalg.slogdet(self.covariance + jitter * np.eye(self.covariance.shape[0]))[1]
+        )
+
+    def information_gain(self, roi_idx, obs_idx, obs_noise_std=None, jitter=DEFAULT_JITTER):  # :151-180
+        roi_idx = np.asarray(roi_idx, dtype=np.int64)
+        obs_idx = np.asarray(obs_idx, dtype=np.int64)
+        prior_covariance = self.covariance[np.ix_(obs_idx, obs_idx)]
+        posterior_covariance = compute_posterior_covariance(
+            prior_covariance=self.covariance, obs_idx=roi_idx, obs_noise_std=None, jitter=jitter
+        )[np.ix_(obs_idx, obs_idx)]
+        obs_noise_mat = noise_covariance_matrix(k=obs_idx.shape[0], noise_std=obs_noise_std)
+        predictive_covariance = prior_covariance + obs_noise_mat
+        posterior_predictive_covariance = posterior_covariance + obs_noise_mat
+        predictive_covariance_log_det = np.linalg.slogdet(predictive_covariance)[1]
+        posterior_predictive_covariance_log_det = np.nan_to_num(
+            np.linalg.slogdet(posterior_predictive_covariance)[1], nan=-np.inf
+        )
+        return 0.5 * np.maximum(predictive_covariance_log_det - posterior_predictive_covariance_log_det, 0)
+
 
 def negative_log_likelihood(K, theta: dict, X, y, noise_std, mean=None):
     """lib/gp/hyperopt.py:14-36 — used only to pin the oracle against the
@@ -418,6 +442,17 @@ class MarginalModel:
 
     def distr(self, i):  # :69-72
         return GaussianDistribution(mean=self._means[i], covariance=self._covariances[i])
+
+    def masked_distr(self, i, mask):  # :74-81
+        mask_idx = set_to_idx(mask)
+        return GaussianDistribution(mean=self._means[i, mask],
+                                    covariance=self._covariances[i][np.ix_(mask_idx, mask_idx)])
+
+    def entropy(self, jitter: float = 0.0):  # :113-117
+        return sum(self.distr(i).entropy(jitter=jitter) for i in range(self.q))
+
+    def masked_entropy(self, mask, jitter: float = 0.0):  # :119-127
+        return sum(self.masked_distr(i, mask).entropy(jitter=jitter) for i in range(self.q))
 
     # -- state ---------------------------------------------------------------
     @property
@@ -872,6 +907,30 @@ class LineBO:
         result["marginal_model"] = model
         result["argmax"] = argmax
         return result
+
+
+# lib/metrics/information_ratio.py:10-57
+def compute_strong_information_ratio(F_max, prev=None):
+    if len(F_max) < 1:
+        return np.array(np.inf)
+    F_max_latest = F_max[-1]
+    new = np.nanmin(np.array(F_max) / F_max_latest)
+    return np.minimum(new, prev) if prev is not None and not np.isnan(prev) else new
+
+
+def compute_information_ratio(model, roi_idx, sample_region_idx):
+    if roi_idx is None:
+        roi_idx = np.arange(model.n)
+    if sample_region_idx is None:
+        sample_region_idx = np.arange(model.n)
+    boundary_idx = sample_region_idx
+    joint_info_gain = 0
+    noise_rates = model.noise_rate.at(model.domain)
+    for i in range(model.q):
+        joint_info_gain += model.distr(i).information_gain(
+            roi_idx=roi_idx, obs_idx=boundary_idx, obs_noise_std=noise_rates[i])
+    indiv_info_gains = itl_directed(model, roi_idx=np.asarray(roi_idx))
+    return np.sum(indiv_info_gains[boundary_idx]) / joint_info_gain
 
 
 def thompson_masks_from_samples(samples, I, J):

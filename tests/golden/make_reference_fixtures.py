@@ -18,6 +18,9 @@ writes
       GaussianDistribution.posterior (jitter and noise paths, repeated indices),
       MarginalModel.step with m = 0, 1, 5, sqd_correlation, the error messages of
       objective_argmax.
+  tests/golden/reference_metrics.npz        SURVEY 8f-4 remainder: entropy / masked_entropy, information_gain,
+      the information ratios and the per-step transductive-learning metrics on a 2-GP model after 3 + 4
+      observations.
   tests/golden/reference_next.npz           SURVEY 8f-2 / 8f-4: ContinuousModel.marginalize before
       and after 7 observations, five LineBO steps along given directions (nested ITL-PM),
       thompson_sampling / thompson_sampling_values on preset samples.
@@ -347,6 +350,57 @@ def next_rows():
     return out
 
 
+def metric_rows():
+    """SURVEY 8f-4 remainder: entropy / masked_entropy (marginal.py:113-127, gaussian_distribution.py:141-149),
+    information_gain (:151-180), information ratios (lib/metrics/information_ratio.py), per-step
+    transductive-learning metrics (lib/metrics/transductive_learning.py)."""
+    from lib.metrics.information_ratio import compute_information_ratio, compute_strong_information_ratio
+    from lib.metrics.transductive_learning import transductive_learning_metrics_generator
+    out = {}
+    rng = np.random.default_rng(21)
+    N, q = 300, 2
+    dom = rng.random((N, 2))
+    noise = HomoscedasticNoise(q, jnp.array([0.1, 0.2]))
+    X0 = dom[[5, 77, 140]]
+    y0 = rng.standard_normal((q, 3))
+    distrs = prior_distr(noise, jnp.array(dom), jnp.array(X0), jnp.array(y0),
+                         [stationary.Matern52(variance=1.0, lengthscale=0.3), stationary.Gaussian(variance=1.5, lengthscale=0.4)],
+                         [ZeroMean()] * q)
+    model = MarginalModel(jr.PRNGKey(3), jnp.array(dom), distrs, beta=jnp.array([2.0, 2.0]), noise_rate=noise)
+    for t in range(4):
+        idx = int(rng.integers(N))
+        model.step(X=model.domain[idx: idx + 1], y=jnp.array(rng.standard_normal((q, 1))))
+    out["m/domain"], out["m/X0"], out["m/y0"] = dom, X0, y0
+    out["m/means"], out["m/covariances"] = np.asarray(model.means), np.asarray(model.covariances)
+    mask = np.zeros(N, dtype=bool)
+    mask[rng.choice(N, 90, replace=False)] = True
+    roi_idx = np.sort(rng.choice(N, 40, replace=False))
+    obs_idx = np.sort(rng.choice(N, 70, replace=False))
+    out["m/mask"], out["m/roi_idx"], out["m/obs_idx"] = mask, roi_idx, obs_idx
+    for jit in (1e-6, 1e-3):
+        out[f"m/entropy/{jit}"] = np.asarray(model.entropy(jitter=jit))
+        out[f"m/masked_entropy/{jit}"] = np.asarray(model.masked_entropy(jnp.array(mask), jitter=jit))
+        out[f"m/distr0_entropy/{jit}"] = np.asarray(model.distr(0).entropy(jitter=jit))
+    out["m/total_variance0"] = np.asarray(model.distr(0).total_variance)
+    ns = jnp.array(0.05 + 0.2 * rng.random(obs_idx.shape[0]))
+    out["m/ig_noise"] = np.asarray(ns)
+    out["m/ig/noisy"] = np.asarray(model.distr(0).information_gain(jnp.array(roi_idx), jnp.array(obs_idx), ns))
+    out["m/ig/scalar"] = np.asarray(model.distr(1).information_gain(jnp.array(roi_idx), jnp.array(obs_idx), jnp.array(0.1)))
+    out["m/ig/overlap"] = np.asarray(model.distr(0).information_gain(jnp.array(roi_idx), jnp.array(roi_idx[:25]), jnp.array(0.3)))
+    # (with a sample region smaller than the domain the reference's call fails: it passes the [n] noise
+    #  vector next to |B| observation indices, information_ratio.py:51-55; only B = domain is defined)
+    out["m/ir/all"] = np.asarray(compute_information_ratio(model, jnp.array(roi_idx), None))
+    fm = [0.9, 0.5, float("nan"), 0.7, 0.25]
+    out["m/sir/list"] = np.asarray(fm)
+    out["m/sir/none"] = np.asarray(compute_strong_information_ratio(fm))
+    out["m/sir/prev"] = np.asarray(compute_strong_information_ratio(fm, prev=1.5))
+    out["m/sir/prevnan"] = np.asarray(compute_strong_information_ratio(fm, prev=float("nan")))
+    mets = transductive_learning_metrics_generator(jnp.array(mask))(model, None, None)
+    for k_, v in mets.items():
+        out[f"m/tl/{k_}"] = np.asarray(v)
+    return out
+
+
 def run_reference_tests():
     import pytest
     plug = os.path.join("/tmp", "refshim_plugin_dir")
@@ -362,7 +416,7 @@ def run_reference_tests():
 
 
 if __name__ == "__main__":
-    stages = sys.argv[1:] or ["tests", "calls", "next", "traj"]
+    stages = sys.argv[1:] or ["tests", "calls", "next", "metrics", "traj"]
     if "tests" in stages:
         run_reference_tests()
     if "calls" in stages:
@@ -373,6 +427,10 @@ if __name__ == "__main__":
         nxt = next_rows()
         np.savez_compressed(os.path.join(HERE, "reference_next.npz"), **nxt)
         print("wrote", len(nxt), "next-row arrays")
+    if "metrics" in stages:
+        met = metric_rows()
+        np.savez_compressed(os.path.join(HERE, "reference_metrics.npz"), **met)
+        print("wrote", len(met), "metric arrays")
     if "traj" in stages:  # minutes: the stand-in's vmap is a Python loop over all N^2 kernel pairs
         traj = {}
         runs = [(name, None) for name in problems.ALL] + [("c2", "CTL"), ("c4", "MMITL"), ("c1", "VTL"), ("c3", "VTL")]

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtal_b200.so")
 STAMP = os.path.join(HERE, ".libtal_b200.stamp")
-SOURCES = ["abi.cu", "rank1.cu", "argmax.cu", "bounds.cu", "score.cu", "gram.cu", "condvar.cu", "condinc.cu", "condapp.cu", "peer.cu", "rankb.cu", "fused.cu", "stepctx.cu"]
+SOURCES = ["abi.cu", "rank1.cu", "argmax.cu", "bounds.cu", "score.cu", "gram.cu", "condvar.cu", "condinc.cu", "condapp.cu", "peer.cu", "rankb.cu", "fused.cu", "stepctx.cu", "dense.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,7 @@
 // sm_100a; tcgen05 has no f64 kind) with cp.async multi-stage staging.
 // m and the column count are padded by the caller to multiples of the tiles.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace tal {
 
@@ -35,20 +36,45 @@ gather_roi_B_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restr
 }
 
 // lower-block storage (one GPU holding all rows): entry (a, col) beyond the end of a's diagonal
-// block is read from its mirror image (col, a)
+// block is read from its mirror image (col, a).  One CTA per 32 x 32 tile of B: the kept part is read
+// along the rows of the target points (coalesced); the mirrored part is a column gather -- one sector
+// per entry whatever the order -- which is read with the lanes running over the target points (the 32
+// sectors of a warp lie in ONE covariance row, instead of 32 rows 8 N bytes apart) and transposed
+// through shared memory so that the writes stay coalesced.
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_roi_B_lower_kernel(const T* __restrict__ cov, i64 ld, i64 N, const i64* __restrict__ roi_idx,
                           i64 m, double* __restrict__ B, i64 ldb, i64 sym_block) {
-  const i64 j = blockIdx.x;
-  const i64 col = (i64)blockIdx.y * blockDim.x + threadIdx.x;
-  if (col >= ldb) return;
-  double v = 0.0;
-  if (j < m && col < N) {
-    const i64 a = roi_idx[j];
-    v = col < (a / sym_block + 1) * sym_block ? (double)cov[a * ld + col] : (double)cov[col * ld + a];
+  __shared__ double tile[32][33];
+  __shared__ i64 a_sm[32];
+  const i64 j0 = (i64)blockIdx.x * 32, col0 = (i64)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (threadIdx.x < 32) a_sm[threadIdx.x] = (j0 + threadIdx.x < m) ? roi_idx[j0 + threadIdx.x] : -1;
+  __syncthreads();
+  const i64 col = col0 + tx;
+  int any_mirror = 0;
+  for (int r = ty; r < 32; r += 8) {  // kept entries + padding, written directly
+    const i64 a = a_sm[r];
+    double v = 0.0;
+    bool direct = true;
+    if (a >= 0 && col < N) {
+      if (col < (a / sym_block + 1) * sym_block) v = (double)cov[a * ld + col];
+      else direct = false;
+    }
+    if (direct) { if (col < ldb) B[(j0 + r) * ldb + col] = v; }
+    else any_mirror = 1;
   }
-  B[j * ldb + col] = v;
+  if (!__syncthreads_or(any_mirror)) return;
+  const i64 a = a_sm[tx];
+  for (int r = ty; r < 32; r += 8) {  // lanes over the target points, one covariance row per warp
+    const i64 c = col0 + r;
+    if (a >= 0 && c < N && c >= (a / sym_block + 1) * sym_block) tile[r][tx] = (double)cov[c * ld + a];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const i64 aj = a_sm[r];
+    if (aj >= 0 && col < N && col >= (aj / sym_block + 1) * sym_block) B[(j0 + r) * ldb + col] = tile[tx][r];
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -397,6 +423,168 @@ potrf_diag_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ L
   }
 }
 
+// (1') The same diagonal-block step on the tensor path (the default; TAL_POTRF_DIAG=0 selects the scalar
+//     kernel above, kept as a cross-check).  The scalar kernel spends 0.21 ms per block in 3 x 128 barrier-
+//     separated dot-product steps on one SM -- 6.7 of the 8.5 ms of a 4,096-point Cholesky.  Here the block is
+//     factored right-looking in 16-column panels inside one CTA of 8 warps:
+//       (a) warp 0 factors the 16 x 16 diagonal block and inverts it, one row (then one column) per lane in
+//           registers, operands exchanged by shuffles;
+//       (b) panel  L_ip = S_ip inv(L_pp)^T  and (c) trailing update  S_ik -= L_ip L_kp^T  as 8 x 8 DMMA
+//           fragments straight out of shared memory (pitch 132 doubles: conflict-free fragment loads);
+//     and the 128 x 128 inverse is assembled by block doubling (16 -> 32 -> 64 -> 128),
+//       inv([[A, 0], [B, C]]) = [[inv A, 0], [-inv C B inv A, inv C]],
+//     two DMMA products per level.  The strictly lower part of the inverse lives TRANSPOSED in the unused
+//     upper triangle of the block's shared-memory copy, its diagonal in a side array.
+constexpr int D2_PA = NB + 4;   // pitch of the block copy
+constexpr int D2_PT = 64 + 4;   // pitch of the product scratch (64 x 64 per level in total)
+constexpr int D2_PD = 16 + 4;   // pitch of the dense 16 x 16 inverse of the current diagonal block
+constexpr int D2_THREADS = 256;
+constexpr int D2_SMEM_BYTES = (NB * D2_PA + 64 * D2_PT + NB + 16 * D2_PD) * (int)sizeof(double);
+
+__device__ __forceinline__ double d2_inv_at(const double* A, const double* invd, int r, int c) {
+  return r > c ? A[c * D2_PA + r] : (r == c ? invd[r] : 0.0);
+}
+
+// warp 0: Cholesky of the 16 x 16 block at (c0, c0) and its inverse
+__device__ __forceinline__ void d2_factor16(double* A, double* invd, double* Dinv, int c0) {
+  const int lane = threadIdx.x & 31;
+  const int r = lane & 15;  // (lanes 16..31 mirror 0..15 and write nothing)
+  double a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = A[(c0 + r) * D2_PA + c0 + k];
+  double myinv = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const double akk = __shfl_sync(0xffffffffu, a[k], k);
+    const double d = sqrt(akk);  // NaN when the block is not positive definite (propagates)
+    const double id = 1.0 / d;
+    const double lrk = (r == k) ? d : a[k] * id;
+    a[k] = lrk;
+    if (r == k) myinv = id;
+#pragma unroll
+    for (int c = k + 1; c < 16; ++c) {
+      const double lck = __shfl_sync(0xffffffffu, lrk, c);
+      a[c] = fma(-lrk, lck, a[c]);  // (entries above the diagonal of a row collect unused values)
+    }
+  }
+  // X = inv(L): lane c holds column c, x[i] = X[i][c] (zero above the diagonal)
+  const int c = r;
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (i == c) ? myinv : 0.0;
+#pragma unroll
+  for (int rr = 1; rr < 16; ++rr) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < rr; ++k) {
+      const double lrk = __shfl_sync(0xffffffffu, a[k], rr);  // L[rr][k]
+      if (k & 1) s1 = fma(lrk, x[k], s1);
+      else s0 = fma(lrk, x[k], s0);
+    }
+    const double irr = __shfl_sync(0xffffffffu, myinv, rr);
+    if (rr > c) x[rr] = -(s0 + s1) * irr;
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k <= r) A[(c0 + r) * D2_PA + c0 + k] = a[k];
+      else A[(c0 + c) * D2_PA + c0 + k] = x[k];  // X[k][c], k > c, transposed into the upper triangle
+      Dinv[k * D2_PD + c] = x[k];
+    }
+    invd[c0 + r] = myinv;
+  }
+}
+
+__global__ void __launch_bounds__(D2_THREADS)
+potrf_diag_mma_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ Linv_all) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int PA = D2_PA, PT = D2_PT, PD = D2_PD;
+  double* A = sm;
+  double* T = A + NB * PA;
+  double* invd = T + 64 * PT;
+  double* Dinv = invd + NB;
+  double* D = S + (i64)j * NB * lds + (i64)j * NB;
+  double* Linv = Linv_all + (i64)j * NB * NB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = threadIdx.x; e < NB * NB; e += D2_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    A[rr * PA + cc] = (cc <= rr) ? D[(i64)rr * lds + cc] : 0.0;
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < NB; c0 += 16) {
+    if (warp == 0) d2_factor16(A, invd, Dinv, c0);
+    __syncthreads();
+    const int nfr = (NB - c0 - 16) / 8;  // 8-row fragments below the diagonal block
+    // (b) panel: rows below times inv(L_pp)^T, in place (a warp owns the rows it rewrites)
+    for (int f = warp; f < nfr; f += 8) {
+      const int rr = c0 + 16 + 8 * f;
+      double av[4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) av[ks] = A[(rr + g) * PA + c0 + ks * 4 + t];
+      double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nf = 0; nf < 2; ++nf)
+          dmma884(acc[nf][0], acc[nf][1], av[ks], Dinv[(nf * 8 + g) * PD + ks * 4 + t]);
+      __syncwarp();
+#pragma unroll
+      for (int nf = 0; nf < 2; ++nf) {
+        A[(rr + g) * PA + c0 + nf * 8 + t * 2] = acc[nf][0];
+        A[(rr + g) * PA + c0 + nf * 8 + t * 2 + 1] = acc[nf][1];
+      }
+    }
+    __syncthreads();
+    // (c) trailing update of the fragments on or below the diagonal
+    for (int fi = warp; fi < nfr; fi += 8) {
+      const int ri = c0 + 16 + 8 * fi;
+      double av[4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) av[ks] = A[(ri + g) * PA + c0 + ks * 4 + t];
+      for (int fk = 0; fk <= fi; ++fk) {
+        const int rk = c0 + 16 + 8 * fk;
+        double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) dmma884(u0, u1, av[ks], A[(rk + g) * PA + c0 + ks * 4 + t]);
+        double* q = A + (ri + g) * PA + rk + t * 2;
+        q[0] -= u0;
+        q[1] -= u1;
+      }
+    }
+    __syncthreads();
+  }
+  // inverse by block doubling; pair pr at level s: blocks [b, b + s) and [b + s, b + 2 s), b = 2 s pr
+  for (int s = 16; s < NB; s *= 2) {
+    const int fr = s / 8, per_pair = fr * fr, total = (NB / (2 * s)) * per_pair;
+    for (int idx = warp; idx < total; idx += 8) {  // T = L21 inv(L11)
+      const int pr = idx / per_pair, w = idx % per_pair, mf = w / fr, nf = w % fr, b = pr * 2 * s;
+      double u0 = 0.0, u1 = 0.0;
+      for (int ks = 0; ks < s / 4; ++ks)
+        dmma884(u0, u1, A[(b + s + mf * 8 + g) * PA + b + ks * 4 + t],
+                d2_inv_at(A, invd, b + ks * 4 + t, b + nf * 8 + g));
+      T[(pr * s + mf * 8 + g) * PT + nf * 8 + t * 2] = u0;
+      T[(pr * s + mf * 8 + g) * PT + nf * 8 + t * 2 + 1] = u1;
+    }
+    __syncthreads();
+    for (int idx = warp; idx < total; idx += 8) {  // X21 = -inv(L22) T, stored transposed
+      const int pr = idx / per_pair, w = idx % per_pair, mf = w / fr, nf = w % fr, b = pr * 2 * s;
+      double u0 = 0.0, u1 = 0.0;
+      for (int ks = 0; ks < s / 4; ++ks)
+        dmma884(u0, u1, d2_inv_at(A, invd, b + s + mf * 8 + g, b + s + ks * 4 + t),
+                T[(pr * s + ks * 4 + t) * PT + nf * 8 + g]);
+      A[(b + nf * 8 + t * 2) * PA + b + s + mf * 8 + g] = -u0;
+      A[(b + nf * 8 + t * 2 + 1) * PA + b + s + mf * 8 + g] = -u1;
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < NB * NB; e += D2_THREADS) {
+    const int rr = e >> 7, cc = e & (NB - 1);
+    if (cc <= rr) D[(i64)rr * lds + cc] = A[rr * PA + cc];
+    Linv[e] = d2_inv_at(A, invd, rr, cc);
+  }
+}
+
 typedef GemmCfg<128, 128, 4, 2, 3> PanelCfg;  // one CTA owns a whole NB x NB block
 typedef GemmCfg<128, 64, 4, 2, 3> SyrkCfg;
 
@@ -438,6 +626,25 @@ potrf_syrk_kernel(double* __restrict__ S, i64 lds, int j) {
   acc_zero<C>(acc);
   gemm_accumulate<C, true>(smem, Lij, lds, Lkj, lds, NB, acc);
   acc_store<C, 1>(Sik, lds, acc);
+}
+
+// (4) C <- C - A A^T on the tiles on or below the diagonal (the Schur complement
+//     Sigma_BB - V_B^T V_B of GaussianDistribution.information_gain,
+//     lib/gp/gaussian_distribution.py:151-180, with A = V_B^T stored [n][K]).
+__global__ void __launch_bounds__(SyrkCfg::THREADS)
+syrk_sub_kernel(double* __restrict__ Cm, i64 ldc, const double* __restrict__ A, i64 lda, int K) {
+  typedef SyrkCfg C;
+  extern __shared__ __align__(16) double smem[];
+  const int p = blockIdx.x;
+  int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= p) ++a;
+  while (a * (a + 1) / 2 > p) --a;
+  const int b = p - a * (a + 1) / 2;  // block row a >= block column b
+  const int n0 = blockIdx.y * C::BN;
+  double acc[C::MF][C::NF][2];
+  acc_zero<C>(acc);
+  gemm_accumulate<C, true>(smem, A + (i64)a * NB * lda, lda, A + ((i64)b * NB + n0) * lda, lda, K, acc);
+  acc_store<C, 1>(Cm + (i64)a * NB * ldc + (i64)b * NB + n0, ldc, acc);
 }
 
 // --------------------------------------------------------------------------
@@ -512,11 +719,11 @@ int tal_gather_roi_lower(const void* cov, long long ld, long long N, const long 
                          long long m, long long m_pad, double jitter, double* S, long long lds,
                          double* B, long long ldb, int dtype, void* stream) {
   TAL_ARG(cov && roi_idx && S && B && m >= 1 && m_pad >= m && m_pad % NB == 0);
-  TAL_ARG(lds >= m_pad && ldb >= N && ldb <= 65535 * 256);
+  TAL_ARG(lds >= m_pad && ldb >= N && ldb <= 65535 * 32);
   TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
   cudaStream_t st = as_stream(stream);
   const i64 blk = tal_sym_block(dtype);
-  dim3 gb((unsigned)m_pad, (unsigned)((ldb + 255) / 256));
+  dim3 gb((unsigned)(m_pad / 32), (unsigned)((ldb + 31) / 32));
   if (dtype == TAL_F64)
     gather_roi_B_lower_kernel<double><<<gb, 256, 0, st>>>((const double*)cov, ld, N, roi_idx, m, B, ldb, blk);
   else
@@ -561,10 +768,17 @@ int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void*
   TAL_ARG(S && work && m_pad >= NB && m_pad % NB == 0 && lds >= m_pad && lds % 2 == 0);
   cudaStream_t st = as_stream(stream);
   static bool a0 = false, a1 = false, a2 = false;
+  static int diag_mma = -1;
+  if (diag_mma < 0) {
+    const char* e = getenv("TAL_POTRF_DIAG");
+    diag_mma = (e && atoi(e) == 0) ? 0 : 1;
+  }
   const int diag_smem = (NB * DIAG_P + NB) * (int)sizeof(double);
   if (!a0) {
     TAL_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   diag_smem));
+    TAL_CUDA(cudaFuncSetAttribute(potrf_diag_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  D2_SMEM_BYTES));
     a0 = true;
   }
   if (set_smem<PanelCfg>(potrf_panel_kernel, a1) != TAL_OK) return TAL_ERR_CUDA;
@@ -572,7 +786,8 @@ int tal_potrf_lower(double* S, long long lds, long long m_pad, void* work, void*
   const int nblk = (int)(m_pad / NB);
   double* Linv = (double*)work;
   for (int j = 0; j < nblk; ++j) {
-    potrf_diag_kernel<<<1, DIAG_THREADS, diag_smem, st>>>(S, lds, j, Linv);
+    if (diag_mma) potrf_diag_mma_kernel<<<1, D2_THREADS, D2_SMEM_BYTES, st>>>(S, lds, j, Linv);
+    else potrf_diag_kernel<<<1, DIAG_THREADS, diag_smem, st>>>(S, lds, j, Linv);
     TAL_LAUNCH_CHECK("tal_potrf_lower/diag");
     const int rem = nblk - j - 1;
     if (rem > 0) {
@@ -595,6 +810,19 @@ int tal_trsm_lower(const double* L, long long lds, long long m_pad, const void* 
   trsm_lower_kernel<<<(unsigned)(n_cols / TrsmCfg::BN), TrsmCfg::THREADS, TrsmCfg::SMEM_BYTES,
                       as_stream(stream)>>>(L, lds, (int)m_pad, (const double*)work, B, ldb);
   TAL_LAUNCH_CHECK("tal_trsm_lower");
+  return TAL_OK;
+}
+
+int tal_syrk_lower_sub(double* Cm, long long ldc, long long n, const double* A, long long lda, long long K,
+                       void* stream) {
+  TAL_ARG(Cm && A && n >= NB && n % NB == 0 && K >= 16 && K % 16 == 0 && ldc >= n && lda >= K);
+  TAL_ARG(ldc % 2 == 0 && lda % 2 == 0);
+  static bool a = false;
+  if (set_smem<SyrkCfg>(syrk_sub_kernel, a) != TAL_OK) return TAL_ERR_CUDA;
+  const long long nb = n / NB;
+  dim3 g((unsigned)(nb * (nb + 1) / 2), NB / SyrkCfg::BN);
+  syrk_sub_kernel<<<g, SyrkCfg::THREADS, SyrkCfg::SMEM_BYTES, as_stream(stream)>>>(Cm, ldc, A, lda, (int)K);
+  TAL_LAUNCH_CHECK("tal_syrk_lower_sub");
   return TAL_OK;
 }
 

@@ -75,17 +75,44 @@ class GaussianDistribution:
                                     storage=self._gp.storage)
 
     def sample(self, key, sample_shape) -> torch.Tensor:
-        """:90-98 — independent functions from the Gaussian: mean + F z with
-        F F^T = covariance from ONE symmetric eigendecomposition (the reference's
-        method="svd" of a PSD matrix) and one GEMM for all samples.  The draws z come
-        from an integer key (lib/_random.py), not threefry."""
+        """:90-98 — independent functions from the Gaussian: mean + L z with L L^T = covariance from ONE
+        blocked DMMA Cholesky (csrc/condvar.cu) and one pass over L for every 8 draws (csrc/dense.cu);
+        the reference runs one SVD of the N x N matrix per draw.  A relative jitter of 1e-8 max(var) keeps the
+        factorisation finite for numerically semi-definite posteriors.  The draws z come from an integer
+        key (lib/_random.py), not threefry: distribution-equivalent only."""
         from lib import _random
         shape = tuple(sample_shape) if not isinstance(sample_shape, int) else (sample_shape,)
         n = self.n
-        w, v = torch.linalg.eigh(self.covariance.to(torch.float64))
-        factor = v * torch.sqrt(torch.clamp(w, min=0.0))[None, :]
-        z = _random.normal(key, shape + (n,))
-        return self.mean + z @ factor.T
+        k = 1
+        for s_ in shape:
+            k *= int(s_)
+        z = _random.normal(key, (k, n))
+        return self._gp.sample(self._slot, z).reshape(shape + (n,))
+
+    @property
+    def total_variance(self) -> torch.Tensor:
+        """:123-127."""
+        return self.variance.sum()
+
+    def entropy(self, jitter: float = 0.0) -> torch.Tensor:
+        """:141-149 — 0.5 (n log(2 pi e) + logdet(covariance + jitter I)); the log-determinant is read off
+        the Cholesky factor (NaN when the matrix is not numerically positive definite, where the
+        reference's LU-based slogdet returns the log of |det|)."""
+        import math
+        n = self.n
+        return 0.5 * (n * math.log(2 * math.pi * math.e) + self._gp.block_logdet(self._slot, None, n, None, float(jitter)))
+
+    def information_gain(self, roi_idx, obs_idx, obs_noise_std=None, jitter: float = DEFAULT_JITTER) -> torch.Tensor:
+        """:151-180 — mutual information of the points `roi_idx` and noisy observations at `obs_idx`."""
+        gp = self._gp
+        roi_idx = torch.as_tensor(roi_idx, device=gp.device).to(torch.int64).reshape(-1).contiguous()
+        obs_idx = torch.as_tensor(obs_idx, device=gp.device).to(torch.int64).reshape(-1).contiguous()
+        ns = None
+        if obs_noise_std is not None:
+            ns = as_f64(obs_noise_std).reshape(-1)
+            if ns.numel() == 1 and obs_idx.numel() > 1:
+                ns = ns.expand(obs_idx.numel()).contiguous()
+        return gp.information_gain(self._slot, roi_idx, int(roi_idx.numel()), obs_idx, int(obs_idx.numel()), ns, jitter)
 
     def _clone(self) -> "GaussianDistribution":
         src = self._gp

@@ -169,6 +169,27 @@ class MarginalModel(Model):
         """:108-111 (no clamping: a negative variance gives NaN)."""
         return torch.sqrt(self._gp.var)
 
+    def masked_distr(self, i: int, mask) -> GaussianDistribution:
+        """:74-81 — GP i limited to the points of `mask` (a copy of the block)."""
+        idx = torch.nonzero(torch.as_tensor(mask, device=self._gp.device).reshape(-1).to(torch.bool))[:, 0]
+        return self.distr(i).sub_distr(idx)
+
+    def entropy(self, jitter: float = 0.0) -> torch.Tensor:
+        """:113-117 — entropy, treating all functions as independent."""
+        return sum(self.distr(i).entropy(jitter=jitter) for i in range(self.q))
+
+    def masked_entropy(self, mask, jitter: float = 0.0) -> torch.Tensor:
+        """:119-127 — entropy within `mask`: the masked block is gathered and factored in place of the
+        reference's `masked_distr(...).entropy()` copy (csrc/dense.cu, csrc/condvar.cu)."""
+        import math
+        gp = self._gp
+        idx = torch.nonzero(torch.as_tensor(mask, device=gp.device).reshape(-1).to(torch.bool))[:, 0].contiguous()
+        m = int(idx.numel())
+        total = torch.zeros((), dtype=torch.float64, device=gp.device)
+        for i in range(self.q):
+            total = total + 0.5 * (m * math.log(2 * math.pi * math.e) + gp.block_logdet(i, idx, m, None, float(jitter)))
+        return total
+
     def sqd_correlation(self, X, A=None) -> torch.Tensor:
         """:129-158 — [q, m, n] squared correlations (small inputs; the CTL /
         MM-ITL rules use the streaming row-reduce kernels instead)."""

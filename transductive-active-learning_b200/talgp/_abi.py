@@ -152,6 +152,11 @@ SIGNATURES = {
     "tal_ctx_observe_y": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
     "tal_fused_scratch_bytes": (_ll, [_i, _ll, _i]),
     "tal_probe_fp64": (_i, [_i, _i, _i, _p, _p]),
+    "tal_gather_sym_block": (_i, [_p, _ll, _ll, _p, _ll, _ll, _p, _d, _p, _ll, _i, _i, _p]),
+    "tal_chol_logdet": (_i, [_p, _ll, _ll, _p, _p]),
+    "tal_tri_sample": (_i, [_p, _ll, _ll, _p, _ll, _i, _p, _p, _ll, _p]),
+    "tal_gather_cols_t": (_i, [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _p]),
+    "tal_syrk_lower_sub": (_i, [_p, _ll, _ll, _p, _ll, _ll, _p]),
 }
 
 _lib = None

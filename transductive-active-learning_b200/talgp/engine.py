@@ -911,6 +911,87 @@ class DeviceGP:
         if st["append"]:
             st["rows"] = rows + 2
 
+    # ------------------------------------------- dense blocks
+    def _need_unsharded(self, what: str) -> None:
+        if self.comm is not None:
+            raise NotImplementedError(f"{what} factors a dense block of the covariance and needs all of its rows "
+                                      "on one GPU (row-sharded models: not built)")
+
+    def block_cholesky(self, i: int, idx: Optional[torch.Tensor], m: int, add_std: Optional[torch.Tensor] = None,
+                       add: float = 0.0, name: str = "blk"):
+        """L = chol(cov_i[idx, idx] + diag(add + add_std^2)) on the DMMA path; returns (S [m_pad, m_pad]
+        with L in its lower triangle, m_pad).  idx None: the leading m x m block."""
+        self._need_unsharded("block_cholesky")
+        self.flush()
+        m_pad = round_up(max(m, 1), 128)
+        S = self._scratch(name + "_S", (m_pad, m_pad))
+        work = self._scratch("cv_work", (int(self.lib.tal_potrf_work_bytes(m_pad)) // 8,))
+        _abi.check(self.lib.tal_gather_sym_block(
+            _ptr(self._cov[i]), self.ld, self.N, _ptr(idx), m, m_pad, _ptr(add_std), float(add), _ptr(S), m_pad,
+            int(self.lower), self.dt, _stream()), "tal_gather_sym_block")
+        _abi.check(self.lib.tal_potrf_lower(_ptr(S), m_pad, m_pad, _ptr(work), _stream()), "tal_potrf_lower")
+        return S, m_pad
+
+    def chol_logdet(self, S: torch.Tensor, m_pad: int, m: int) -> torch.Tensor:
+        """slogdet of the factored block: 2 sum log diag(L) (device scalar)."""
+        out = torch.empty((1,), dtype=torch.float64, device=self.device)
+        _abi.check(self.lib.tal_chol_logdet(_ptr(S), m_pad, m, _ptr(out), _stream()), "tal_chol_logdet")
+        return out[0]
+
+    def block_logdet(self, i: int, idx: Optional[torch.Tensor], m: int, add_std=None, add: float = 0.0) -> torch.Tensor:
+        if m == 0:
+            return torch.zeros((), dtype=torch.float64, device=self.device)
+        S, m_pad = self.block_cholesky(i, idx, m, add_std, add)
+        return self.chol_logdet(S, m_pad, m)
+
+    def sample(self, i: int, z: torch.Tensor, rel_jitter: float = 1e-8) -> torch.Tensor:
+        """mean_i + L z for k draws z [k, N] with L L^T = cov_i + jitter I: one Cholesky and one pass over L
+        for every 8 draws.  jitter = rel_jitter * max(var), raised 100x (up to three times) while the factor
+        is not finite (the reference's SVD accepts a numerically indefinite matrix, Cholesky does not)."""
+        N = self.N
+        z = z.to(device=self.device, dtype=torch.float64).contiguous()
+        k = z.shape[0]
+        scale = float(self.var[i].max())
+        for attempt in range(4):
+            S, m_pad = self.block_cholesky(i, None, N, add=rel_jitter * scale * (100.0 ** attempt), name="smp")
+            if bool(torch.isfinite(torch.diagonal(S)[:N]).all()):
+                break
+        out = torch.empty((k, N), dtype=torch.float64, device=self.device)
+        _abi.check(self.lib.tal_tri_sample(_ptr(S), m_pad, N, _ptr(z), N, k, _ptr(self.mean[i]), _ptr(out), N,
+                                           _stream()), "tal_tri_sample")
+        return out
+
+    def information_gain(self, i: int, roi_idx: torch.Tensor, m: int, obs_idx: torch.Tensor, nb: int,
+                         obs_noise_std: Optional[torch.Tensor], jitter: float = 1e-5) -> torch.Tensor:
+        """0.5 max(logdet(Sigma_BB + D) - logdet(Sigma_BB - Sigma_BA (Sigma_AA + jitter^2 I)^-1 Sigma_AB + D), 0)
+        (GaussianDistribution.information_gain, lib/gp/gaussian_distribution.py:151-180): gather -> Cholesky ->
+        forward TRSM (the conditioning kernels of directed ITL) -> SYRK of the columns B -> two Choleskys."""
+        self._need_unsharded("information_gain")
+        lib = self.lib
+        obs_idx = obs_idx.to(device=self.device, dtype=torch.int64).contiguous()
+        if obs_noise_std is not None:
+            obs_noise_std = obs_noise_std.to(device=self.device, dtype=torch.float64).contiguous()
+        add = 0.0  # noise_covariance_matrix(k, None) has default = 0 (lib/utils.py:44-50)
+        prior_ld = self.block_logdet(i, obs_idx, nb, obs_noise_std, add)
+        nb_pad = round_up(nb, 128)
+        P = self._scratch("ig_P", (nb_pad, nb_pad))
+        _abi.check(lib.tal_gather_sym_block(_ptr(self._cov[i]), self.ld, self.N, _ptr(obs_idx), nb, nb_pad,
+                                            _ptr(obs_noise_std), add, _ptr(P), nb_pad, int(self.lower), self.dt,
+                                            _stream()), "tal_gather_sym_block")
+        if m > 0:
+            m_pad, ncols = self._cond_dims(m)
+            V = self._scratch("cv_B", (m_pad, ncols))
+            self.cond_var_sumsq(i, roi_idx, m, jitter, V=V)
+            Vt = self._scratch("ig_Vt", (nb_pad, m_pad))
+            _abi.check(lib.tal_gather_cols_t(_ptr(V), ncols, m_pad, _ptr(obs_idx), nb, nb_pad, _ptr(Vt), m_pad,
+                                             _stream()), "tal_gather_cols_t")
+            _abi.check(lib.tal_syrk_lower_sub(_ptr(P), nb_pad, nb_pad, _ptr(Vt), m_pad, m_pad, _stream()),
+                       "tal_syrk_lower_sub")
+        work = self._scratch("cv_work", (int(lib.tal_potrf_work_bytes(nb_pad)) // 8,))
+        _abi.check(lib.tal_potrf_lower(_ptr(P), nb_pad, nb_pad, _ptr(work), _stream()), "tal_potrf_lower")
+        post_ld = torch.nan_to_num(self.chol_logdet(P, nb_pad, nb), nan=-np.inf)  # :175-177
+        return 0.5 * torch.clamp(prior_ld - post_ld, min=0.0)
+
     def drop_conditioning(self) -> None:
         self._sel_discard()
         self._cond = None
