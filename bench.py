@@ -594,6 +594,7 @@ def run_itl(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, war
     if want_e2e:
         class HostFunction(Function):
             q, first_constraint = 1, 1
+            host_input = True  # X arrives as a host array (the model's host copy of the domain row)
 
             def observe(self, X):  # X: [1, d] device tensor -> D2H; returns host array [q, 1]
                 x = X.cpu().numpy()
@@ -621,7 +622,7 @@ def run_itl(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, war
         e2e_ms = float(_max_over_ranks(e2e_ms, dev, world)[0])
         assert np.isfinite(fmax)
         e2e = {"value": steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": 8 * model.q,
-               "d2h_bytes_per_step": 32 + 8 * w["d"],  # arg-max record + selected point
+               "d2h_bytes_per_step": 32,  # the arg-max record (the selected point is a row of the host copy of the domain)
                "ms_per_step": e2e_ms / steps,
                "api": "lib.algorithms.itl.ITL.step(f) with a host black box on every rank"}
     if rank != 0:

@@ -279,6 +279,14 @@ int tal_colsum_lower(int rule, const void* cov, long long ld, long long row0, lo
                      long long N, const long long* roi_idx, long long m, const double* row_weight,
                      const double* dinv, double p0, double p1, double* part, int n_split,
                      double* c_out, int dtype, void* stream);
+/* the same for an ROI that covers a large part of the domain (the potential-maximiser ROIs of the Safe-BO
+ * configurations, lib/algorithms/__init__.py:140-147: m ~ N): the mirrored part of every row is streamed and
+ * masked by roi_mask (one byte per point) instead of gathered entry by entry; w_pt = row_weight by point
+ * ([N], NULL with row_weight NULL). */
+int tal_colsum_lower_dense(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                           long long N, const long long* roi_idx, long long m, const unsigned char* roi_mask,
+                           const double* row_weight, const double* w_pt, const double* dinv, double p0,
+                           double p1, double* part, int n_split, double* c_out, int dtype, void* stream);
 int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,
                   void* stream);
 int tal_roi_weights(const double* var, const long long* roi_idx, long long m, int reciprocal,

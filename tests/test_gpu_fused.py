@@ -314,3 +314,51 @@ def test_append_form_long_horizon_drift(cuda):
     print(f"append form after {t + 1} observations without a re-base: max relative drift of cs vs re-based every 64 = "
           f"{drift:.2e}; scores vs from-scratch conditioning = {rel:.2e}; near-tie partings = {near}")
     assert drift < 1e-6 and rel < 1e-5
+
+
+@pytest.mark.parametrize("storage", ["lower", "full"])
+def test_greedy_step_with_host_black_boxes_matches_device_black_box(cuda, storage):
+    """ITL.step(f) through the drop-in API: a device-resident black box takes the one-call fused step, any
+    other black box is asked for y while the device already works on the y-independent part of the update
+    (tal_ctx_observe without y, then tal_ctx_observe_y + selection).  Same selections and bit-identical
+    model state, with the input handed over as a device tensor or as a host copy (`host_input`)."""
+    import problems
+    from lib.function import Function
+    p = problems.c3(T=24)
+    table = p["table"]
+    dom_np = p["domain"]
+
+    class HostBox(Function):
+        q, first_constraint = 1, 1
+
+        def __init__(self, host_input):
+            self.host_input = host_input
+            self.seen = []
+
+        def observe(self, X):
+            assert X.is_cuda != self.host_input
+            x = X.cpu().numpy()
+            i = int(np.argmin(np.linalg.norm(dom_np - x, axis=1)))
+            self.seen.append(i)
+            return table[:, [i]]
+
+    runs = []
+    for box in (None, HostBox(False), HostBox(True)):
+        model, alg, f_dev = problems.build_cuda(p, storage=storage)
+        f = f_dev if box is None else box
+        sel, fmax = [], []
+        for t in range(p["T"]):
+            res = alg.step(f)
+            sel.append(model.last_argmax.idx)
+            fmax.append(float(res["F_max"]))
+            assert np.allclose(np.asarray(res["x"].cpu()), dom_np[sel[-1]])
+        model._gp.flush()
+        runs.append((sel, fmax, model))
+        if box is not None:
+            assert box.seen == sel
+    (s0, f0, m0) = runs[0]
+    for s, fm, m in runs[1:]:
+        assert s == s0
+        np.testing.assert_allclose(fm, f0, rtol=1e-12)
+        _same_state(m._gp, m0._gp, cuda)
+    assert m0.t == p["T"]

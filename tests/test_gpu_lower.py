@@ -160,3 +160,30 @@ def test_lower_fullsize_properties_n65536(cuda):
         del gp
         torch.cuda.empty_cache()
     assert sels["lower"] == sels["full"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("frac", [0.3, 1.0])
+def test_dense_roi_row_reduce_lower_matches_full(cuda, dtype, frac):
+    """ROIs that cover a large part of the domain (potential maximisers: m ~ N) take the streamed + masked
+    form of the mirrored column sums (tal_colsum_lower_dense); same scores as full storage for all four rules,
+    with the mask supplied (ROI.from_mask) or rebuilt from the index list."""
+    from talgp import _abi
+    N = 2100
+    (full, low), rng = _pair(cuda, N, 2, dtype, seed=5)
+    ys = rng.standard_normal((3, 2))
+    for g in (full, low):  # a few observations so that the matrices are not the bare Gram matrices
+        for t, idx in enumerate((7, 900, 2050)):
+            g.observe(idx, ys[t], [2.0, 2.0])
+    m = int(frac * N)
+    roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
+    mask = torch.zeros((N,), dtype=torch.uint8, device=cuda)
+    mask[roi] = 1
+    tol = dict(rtol=1e-11, atol=1e-12) if dtype == torch.float64 else dict(rtol=2e-5, atol=1e-6)
+    for rule, kw in ((_abi.RULE_VTL, {}), (_abi.RULE_CTL, {}), (_abi.RULE_MMITL, {}),
+                     (_abi.RULE_TRUVAR, dict(p0=[1.5, 1.5], p1=0.01))):
+        Ff = full.score_rows(rule, roi, m, **kw)
+        Fl = low.score_rows(rule, roi, m, roi_mask=mask, **kw)
+        Fl2 = low.score_rows(rule, roi, m, **kw)
+        torch.testing.assert_close(Fl, Ff, **tol)
+        assert torch.equal(Fl, Fl2)

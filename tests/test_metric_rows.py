@@ -1,0 +1,122 @@
+"""SURVEY 8f-4 remainder -- entropy / masked_entropy (lib/model/marginal.py:113-127,
+lib/gp/gaussian_distribution.py:141-149), information_gain (:151-180), the information ratios
+(lib/metrics/information_ratio.py) and the per-step transductive-learning metrics
+(lib/metrics/transductive_learning.py) -- against golden vectors produced by the reference's own source
+(tests/golden/reference_metrics.npz, made by tests/golden/make_reference_fixtures.py metrics): the oracle on
+the CPU tier, the CUDA path (block gather -> DMMA Cholesky -> log-determinant / SYRK, csrc/dense.cu +
+csrc/condvar.cu) on the GPU tier.  Plus the device sampler: mean + L z with the DMMA Cholesky factor."""
+import os
+
+import numpy as np
+import pytest
+
+M = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_metrics.npz"))
+JITS = ("1e-06", "0.001")
+# log-determinants of 300 x 300 posterior covariances with eigenvalues down to the jitter: Cholesky and LU agree
+# to ~cond * eps relative to the entries; the tolerance below is on the entropy (a sum of 300 logs)
+TOL = dict(rtol=1e-8, atol=1e-7)
+
+
+def _oracle_model():
+    import oracle as O
+    q = 2
+    noise = O.HomoscedasticNoise(q, np.array([0.1, 0.2]))
+    distrs = [O.GaussianDistribution(M["m/means"][i], M["m/covariances"][i]) for i in range(q)]
+    return O, O.MarginalModel(0, M["m/domain"], distrs, beta=np.array([2.0, 2.0]), noise_rate=noise)
+
+
+def _cuda_model(storage="full"):
+    import torch
+    from lib.gp.gaussian_distribution import GaussianDistribution
+    from lib.model.marginal import MarginalModel
+    from lib.noise import HomoscedasticNoise
+    q = 2
+    noise = HomoscedasticNoise(q, np.array([0.1, 0.2]))
+    distrs = [GaussianDistribution(torch.as_tensor(M["m/means"][i], device="cuda"),
+                                   torch.as_tensor(M["m/covariances"][i], device="cuda"), storage=storage)
+              for i in range(q)]
+    return MarginalModel(0, M["m/domain"], distrs, beta=np.array([2.0, 2.0]), noise_rate=noise)
+
+
+def _f(x):
+    return float(x.detach().cpu()) if hasattr(x, "detach") else float(x)
+
+
+def test_oracle_entropy_and_information_gain_match_reference():
+    O, model = _oracle_model()
+    for j in JITS:
+        np.testing.assert_allclose(model.entropy(jitter=float(j)), M[f"m/entropy/{j}"], **TOL)
+        np.testing.assert_allclose(model.masked_entropy(M["m/mask"], jitter=float(j)), M[f"m/masked_entropy/{j}"], **TOL)
+        np.testing.assert_allclose(model.distr(0).entropy(jitter=float(j)), M[f"m/distr0_entropy/{j}"], **TOL)
+    roi, obs = M["m/roi_idx"], M["m/obs_idx"]
+    np.testing.assert_allclose(model.distr(0).information_gain(roi, obs, M["m/ig_noise"]), M["m/ig/noisy"], rtol=1e-9)
+    np.testing.assert_allclose(model.distr(1).information_gain(roi, obs, np.array(0.1)), M["m/ig/scalar"], rtol=1e-9)
+    np.testing.assert_allclose(model.distr(0).information_gain(roi, roi[:25], np.array(0.3)), M["m/ig/overlap"], rtol=1e-9)
+    np.testing.assert_allclose(O.compute_information_ratio(model, roi, None), M["m/ir/all"], rtol=1e-7)
+    fm = list(M["m/sir/list"])
+    np.testing.assert_allclose(O.compute_strong_information_ratio(fm), M["m/sir/none"])
+    np.testing.assert_allclose(O.compute_strong_information_ratio(fm, prev=1.5), M["m/sir/prev"])
+    np.testing.assert_allclose(O.compute_strong_information_ratio(fm, prev=float("nan")), M["m/sir/prevnan"])
+    assert float(O.compute_strong_information_ratio([])) == np.inf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("storage", ["full", "lower"])
+def test_cuda_entropy_matches_reference(cuda, storage):
+    model = _cuda_model(storage)
+    for j in JITS:
+        np.testing.assert_allclose(_f(model.entropy(jitter=float(j))), M[f"m/entropy/{j}"], **TOL)
+        np.testing.assert_allclose(_f(model.masked_entropy(M["m/mask"], jitter=float(j))), M[f"m/masked_entropy/{j}"], **TOL)
+        np.testing.assert_allclose(_f(model.distr(0).entropy(jitter=float(j))), M[f"m/distr0_entropy/{j}"], **TOL)
+        np.testing.assert_allclose(_f(model.masked_distr(1, M["m/mask"]).entropy(jitter=float(j)))
+                                   + _f(model.masked_distr(0, M["m/mask"]).entropy(jitter=float(j))),
+                                   M[f"m/masked_entropy/{j}"], **TOL)
+    np.testing.assert_allclose(_f(model.distr(0).total_variance), M["m/total_variance0"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("storage", ["full", "lower"])
+def test_cuda_information_gain_and_ratios_match_reference(cuda, storage):
+    import torch
+    from lib.metrics.information_ratio import compute_information_ratio, compute_strong_information_ratio
+    from lib.metrics.transductive_learning import transductive_learning_metrics_generator
+    model = _cuda_model(storage)
+    roi, obs = M["m/roi_idx"], M["m/obs_idx"]
+    # the posterior block Sigma_BB - V_B^T V_B has eigenvalues down to jitter^2 = 1e-10 next to the noise
+    np.testing.assert_allclose(_f(model.distr(0).information_gain(roi, obs, M["m/ig_noise"])), M["m/ig/noisy"], rtol=1e-8)
+    np.testing.assert_allclose(_f(model.distr(1).information_gain(roi, obs, np.array(0.1))), M["m/ig/scalar"], rtol=1e-8)
+    np.testing.assert_allclose(_f(model.distr(0).information_gain(roi, roi[:25], np.array(0.3))), M["m/ig/overlap"], rtol=1e-8)
+    np.testing.assert_allclose(_f(compute_information_ratio(model, torch.as_tensor(roi, device=cuda), None)), M["m/ir/all"],
+                               rtol=1e-6)
+    fm = list(M["m/sir/list"])
+    np.testing.assert_allclose(_f(compute_strong_information_ratio(fm)), M["m/sir/none"])
+    np.testing.assert_allclose(_f(compute_strong_information_ratio(fm, prev=1.5)), M["m/sir/prev"])
+    np.testing.assert_allclose(_f(compute_strong_information_ratio(fm, prev=float("nan"))), M["m/sir/prevnan"])
+    assert _f(compute_strong_information_ratio([])) == np.inf
+    mets = transductive_learning_metrics_generator(M["m/mask"])(model, None, None)
+    for k in ("entropy_in_roi", "max_stddev_in_roi", "avg_stddev_in_roi"):
+        np.testing.assert_allclose(_f(mets[k]), M[f"m/tl/{k}"], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_cuda_sampler_is_a_cholesky_factor_of_the_covariance(cuda):
+    """x = mean + L z with L from the DMMA Cholesky: for z = e_c the draw is mean + L[:, c], so feeding the
+    identity recovers L, and L L^T must be the covariance (+ the documented relative jitter 1e-8 max var)."""
+    import torch
+    model = _cuda_model()
+    gp = model._gp
+    n = model.n
+    z = torch.eye(n, dtype=torch.float64, device=cuda)
+    L = (gp.sample(0, z) - gp.mean[0][None, :]).T  # column c of L from draw c
+    assert bool(torch.equal(L, torch.tril(L)))
+    cov = torch.as_tensor(M["m/covariances"][0], device=cuda)
+    recon = L @ L.T
+    jit = 1e-8 * float(gp.var[0].max())
+    torch.testing.assert_close(recon, cov + jit * torch.eye(n, dtype=torch.float64, device=cuda), rtol=1e-9, atol=1e-11)
+    # and through the public API: shapes, determinism per key, moments
+    d0 = model.distr(0)
+    s1, s2 = d0.sample(key=5, sample_shape=(3, 2)), d0.sample(key=5, sample_shape=(3, 2))
+    assert s1.shape == (3, 2, n) and bool(torch.equal(s1, s2))
+    s = d0.sample(key=9, sample_shape=(4000,))
+    emp = torch.cov(s.T)
+    assert float((emp - cov).abs().max()) < 0.12 and float((s.mean(0) - d0.mean).abs().max()) < 0.08

@@ -138,6 +138,52 @@ colsum_cols_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, const i64* __re
   if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
 }
 
+// The same mirrored sums when the ROI is a large part of the domain (potential-maximiser ROIs of the
+// Safe-BO configurations: m ~ N): instead of gathering m indexed entries per row -- one dependent
+// index + value load per lane and iteration, latency-bound -- the kept part of row x is STREAMED with
+// 16-byte loads and masked by the ROI's byte mask (64 KB, L1-resident); by-point weights w_pt only for
+// the rules that have them.  One warp per local row, UNROLL vectors in flight per lane.
+template <typename T, int RULE, bool HAS_W>
+__global__ void __launch_bounds__(256)
+colsum_cols_dense_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, i64 N,
+                         const unsigned char* __restrict__ roi_mask, const double* __restrict__ w_pt,
+                         const double* __restrict__ dinv, double p0, double p1, double* __restrict__ out,
+                         i64 sym_block, i64 row0, int accumulate) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
+  constexpr int UNROLL = 4;
+  const i64 r = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n_loc) return;
+  const T* row = cov + r * ld;
+  const double di = dinv ? dinv[r] : 0.0;
+  i64 a_end = sym_block > 0 ? ((row0 + r) / sym_block) * sym_block : N;  // (a multiple of 32 / the row length)
+  if (a_end > N) a_end = N;
+  double acc = 0.0;
+  for (i64 c0 = (i64)lane * VN; c0 < a_end; c0 += (i64)32 * VN * UNROLL) {
+    V v[UNROLL];
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      const i64 c = c0 + (i64)t * 32 * VN;
+      if (c < a_end) v[t] = ld_stream(reinterpret_cast<const V*>(row + c));
+    }
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      const i64 c = c0 + (i64)t * 32 * VN;
+      if (c < a_end) {
+        T e[VN];
+        memcpy(e, &v[t], sizeof(V));
+#pragma unroll
+        for (int k = 0; k < VN; ++k)
+          if (c + k < a_end && roi_mask[c + k])
+            acc += elem<RULE>((double)e[k], HAS_W ? w_pt[c + k] : 1.0, di, p0, p1);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+}
+
 // tr_A = sum_{a in roi} var[a]  (one block, deterministic)
 __global__ void __launch_bounds__(256)
 roi_trace_kernel(const double* __restrict__ var, const i64* __restrict__ roi_idx, i64 m,
@@ -328,6 +374,46 @@ int tal_colsum_lower(int rule, const void* cov, long long ld, long long row0, lo
   if (rc != TAL_OK) return rc;
   return colsum_cols_impl(rule, cov, ld, n_loc, roi_idx, m, row_weight, dinv ? dinv + row0 : nullptr, p0,
                           p1, c_out + row0, dtype, stream, blk, row0, 1);
+}
+
+/* tal_colsum_lower for an ROI that covers a large part of the domain: the mirrored part is streamed and
+ * masked (roi_mask: one byte per point; w_pt: by-point weights [N] or NULL = 1) instead of gathered. */
+int tal_colsum_lower_dense(int rule, const void* cov, long long ld, long long row0, long long n_loc,
+                           long long N, const long long* roi_idx, long long m, const unsigned char* roi_mask,
+                           const double* row_weight, const double* w_pt, const double* dinv, double p0,
+                           double p1, double* part, int n_split, double* c_out, int dtype, void* stream) {
+  TAL_ARG(roi_mask && ((row_weight == nullptr) == (w_pt == nullptr)));
+  const i64 blk = tal_sym_block(dtype);
+  int rc = colsum_rows_impl(rule, cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, p1, part,
+                            n_split, c_out, dtype, stream, blk);
+  if (rc != TAL_OK) return rc;
+  if (n_loc == 0) return TAL_OK;
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)((n_loc + 7) / 8);
+  const double* dv = dinv ? dinv + row0 : nullptr;
+#define TAL_CD(T, R)                                                                                         \
+  do {                                                                                                       \
+    if (w_pt) colsum_cols_dense_kernel<T, R, true><<<grid, 256, 0, st>>>((const T*)cov, ld, n_loc, N, roi_mask, \
+        w_pt, dv, p0, p1, c_out + row0, blk, row0, 1);                                                        \
+    else colsum_cols_dense_kernel<T, R, false><<<grid, 256, 0, st>>>((const T*)cov, ld, n_loc, N, roi_mask,    \
+        w_pt, dv, p0, p1, c_out + row0, blk, row0, 1);                                                        \
+  } while (0)
+  if (dtype == TAL_F64) {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_CD(double, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_CD(double, TAL_RULE_MMITL); break;
+      default: TAL_CD(double, TAL_RULE_TRUVAR); break;
+    }
+  } else {
+    switch (rule) {
+      case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_CD(float, TAL_RULE_VTL); break;
+      case TAL_RULE_MMITL: TAL_CD(float, TAL_RULE_MMITL); break;
+      default: TAL_CD(float, TAL_RULE_TRUVAR); break;
+    }
+  }
+#undef TAL_CD
+  TAL_LAUNCH_CHECK("tal_colsum_lower_dense");
+  return TAL_OK;
 }
 
 int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,

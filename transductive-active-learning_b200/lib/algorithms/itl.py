@@ -37,9 +37,23 @@ class ITL(DirectedDiscreteGreedyAlgorithm):
                 F = gp._scratch("ctx_F", (gp.n_cand,)).clone()  # (the update below overwrites it with the next scores)
                 if gp.sharded and self.gather_F:
                     F = gp.gather_candidates(F)
-                X = model.domain[idx: idx + 1]
-                y = f.observe(X)
-                model._step_index(rec[0:1], y, auto_select=True)
+                # a device-resident black box (a lookup: no host round trip) gets the whole update as one fused
+                # call; any other black box is asked for y WHILE the device does everything that does not need
+                # it (observed row, weights, variances, conditioning pass: ~all of the step), then the means /
+                # bounds and the selection of the next candidate are enqueued behind it
+                if getattr(f, "host_input", False):
+                    X = torch.from_numpy(model.domain_host()[idx: idx + 1])
+                else:
+                    X = model.domain[idx: idx + 1]
+                if getattr(f, "device_resident", False):
+                    y = f.observe(X)
+                    model._step_index(rec[0:1], y, auto_select=True)
+                else:
+                    model._step_index_begin(rec[0:1])
+                    y = f.observe(X)
+                    model._step_index_end(rec[0:1], y)
+                    if gp._cond is not None and gp._cond["valid"]:
+                        gp.ctx_select(model.first_constraint, model._safe_override(), self.sample_mask())
                 if not isinstance(y, torch.Tensor):
                     import numpy as np
                     y = torch.as_tensor(np.asarray(y, dtype=np.float64))

@@ -15,4 +15,4 @@ class TruVar(DirectedDiscreteGreedyAlgorithm):
         roi = self.roi
         self.model.update_variance_threshold(roi)
         beta = float(np.asarray(self.model._beta_now())[0])
-        return self.model._gp.score_rows(_abi.RULE_TRUVAR, roi.idx, roi.m, p0=[beta], p1=float(self.model.eta) ** 2)
+        return self.model._gp.score_rows(_abi.RULE_TRUVAR, roi.idx, roi.m, p0=[beta], p1=float(self.model.eta) ** 2, roi_mask=roi.mask)

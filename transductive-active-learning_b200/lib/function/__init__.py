@@ -17,6 +17,8 @@ class TableFunction(Function):
     lookup, so a benchmark / parity harness sees identical observations on
     every implementation and the BO loop needs no host round trip."""
 
+    device_resident = True  # `observe` never leaves the device: the greedy step stays one fused call
+
     def __init__(self, model_domain, y_table, first_constraint: int = 1):
         from lib._device import as_f64
         self.domain = as_f64(model_domain)

@@ -374,6 +374,28 @@ class MarginalModel(Model):
         self._gp.observe(idx_dev, yv, beta, auto_select=auto_select)
         self._t += 1
 
+    def _step_index_begin(self, idx_dev: torch.Tensor) -> None:
+        """The part of `step` for one observation that does not depend on its value (:350-368: the observed
+        row, the weights, the variances, the conditioning state and the queued covariance update): a host
+        black box is asked for y while the device works on this."""
+        self._gp.ctx_observe(idx_dev, 0, None, 1, False, self._beta_now())  # beta at the OLD t (:366-368)
+
+    def _step_index_end(self, idx_dev: torch.Tensor, y) -> None:
+        """... and the part that does: means and confidence bounds."""
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            yv = y.reshape(-1)[: self.q] if y.numel() == self.q else y[:, 0].contiguous()
+        else:
+            yv = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y, dtype=np.float64).reshape(self.q, -1)[:, 0]
+        gp = self._gp
+        gp.ctx_observe_y(idx_dev, 0, gp.stage_y(yv), 1, False)
+        self._t += 1
+
+    def domain_host(self) -> np.ndarray:
+        """Host copy of the domain (made once): a host black box gets its input without a device round trip."""
+        if getattr(self, "_domain_host", None) is None:
+            self._domain_host = self.domain.detach().cpu().numpy()
+        return self._domain_host
+
     def _argmax_index(self, F: torch.Tensor, sample_mask: Optional[torch.Tensor] = None):
         """Masked arg-max kernel + the reference's three error checks
         (:336-342).  F is overwritten with the sample-region-masked objective."""

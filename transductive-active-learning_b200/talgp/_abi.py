@@ -97,6 +97,8 @@ SIGNATURES = {
                              _i, _p]),
     "tal_colsum_lower": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p,
                               _i, _p]),
+    "tal_colsum_lower_dense": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _p, _p, _d, _d, _p, _i, _p,
+                                    _i, _p]),
     "tal_colsum_cols": (_i, [_i, _p, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p]),
     "tal_roi_trace": (_i, [_p, _p, _ll, _p, _p]),
     "tal_roi_weights": (_i, [_p, _p, _ll, _i, _p, _p]),

@@ -543,6 +543,22 @@ class DeviceGP:
             _ptr(self.kbuf), _ptr(self.wbuf), self.dt_upd,
             self.rank1_variant if variant is None else variant, _stream()), "tal_rank1_update")
 
+    def stage_y(self, y) -> torch.Tensor:
+        """Device copy of an observation y[q]: a device tensor is used as it is, a host value goes through the
+        pinned staging buffer into a fresh slot of a device ring (asynchronous H2D, q * 8 bytes)."""
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            return y
+        if self._y_event is not None:
+            self._y_event.synchronize()  # the previous async copy out of the pinned buffer is done
+        self._y_host.copy_(torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1)))
+        self._y_slot = (self._y_slot + 1) % self._y_dev.shape[0]
+        y_dev = self._y_dev[self._y_slot]  # a fresh device slot: earlier steps may still read theirs
+        y_dev.copy_(self._y_host, non_blocking=True)
+        if self._y_event is None:
+            self._y_event = torch.cuda.Event()
+        self._y_event.record()
+        return y_dev
+
     def observe(self, idx, y, beta: Sequence[float], y_gather: bool = False,
                 y_stride: int = 1, allreduce=None, auto_select: bool = False) -> None:
         """One observation at domain index `idx` (python int or 1-element int64
@@ -553,18 +569,7 @@ class DeviceGP:
             idx_dev, idx_host = idx, 0
         else:
             idx_dev, idx_host = None, int(idx)
-        if isinstance(y, torch.Tensor) and y.is_cuda:
-            y_dev = y
-        else:
-            if self._y_event is not None:
-                self._y_event.synchronize()  # the previous async copy out of the pinned buffer is done
-            self._y_host.copy_(torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1)))
-            self._y_slot = (self._y_slot + 1) % self._y_dev.shape[0]
-            y_dev = self._y_dev[self._y_slot]  # a fresh device slot: earlier steps may still read theirs
-            y_dev.copy_(self._y_host, non_blocking=True)
-            if self._y_event is None:
-                self._y_event = torch.cuda.Event()
-            self._y_event.record()
+        y_dev = self.stage_y(y)
         if allreduce is None and self._ctx_usable():
             self.ctx_observe(idx_dev, idx_host, y_dev, y_stride, y_gather, beta, auto_select=auto_select)
             return
@@ -665,7 +670,7 @@ class DeviceGP:
         return int(max(1, min(64, m, -(-1184 // col_tiles))))
 
     def score_rows(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0,
-                   sharded_cols: bool = False) -> torch.Tensor:
+                   sharded_cols: bool = False, roi_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """F over this shard's candidates for the row-reduce rules (VTL, CTL,
         MM-ITL, TruVar).  One GPU: F is [N]; row-sharded with `sharded_cols`:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
@@ -673,7 +678,7 @@ class DeviceGP:
         N = self.N
         self.flush()
         if self.lower:
-            return self._score_rows_lower(rule, roi_idx, m, p0, p1)
+            return self._score_rows_lower(rule, roi_idx, m, p0, p1, roi_mask)
         sharded_cols = sharded_cols or self.sharded
         n_out = self.n_loc if sharded_cols else N
         off = self.row0 if sharded_cols else 0
@@ -718,7 +723,8 @@ class DeviceGP:
                 1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
         return F
 
-    def _score_rows_lower(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0) -> torch.Tensor:
+    def _score_rows_lower(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0,
+                          roi_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The row-reduce rules in lower-block storage: every pair (a, x) of a target point and a
         candidate is kept either in row a (x below the end of a's diagonal block) or in row x;
         `tal_colsum_lower` sums what this shard keeps over all N candidates, a sum over the shards
@@ -739,19 +745,37 @@ class DeviceGP:
         dinv = self._scratch("score_dinv", (N,)) if need_dinv else None
         n_split = self._n_split(m)
         part = self._scratch("score_part", (n_split, N))
+        # an ROI that covers a large part of the domain (m ~ N for the potential maximisers of the Safe-BO
+        # configurations): stream + mask the mirrored part instead of gathering it entry by entry
+        dense = 4 * m >= N
+        if dense:
+            if roi_mask is None or roi_mask.numel() != N:
+                roi_mask = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+                roi_mask[roi_idx[:m]] = 1
+            roi_mask = roi_mask.view(torch.uint8) if roi_mask.dtype == torch.bool else roi_mask
+            w_pt = self._scratch("score_w_pt", (N,)) if need_w else None
         for i in range(self.q):
             if need_w:
                 _abi.check(lib.tal_roi_weights(_ptr(self.var[i]), _ptr(roi_idx), m,
                                                0 if rule == _abi.RULE_TRUVAR else 1, _ptr(w),
                                                _stream()), "tal_roi_weights")
+                if dense:
+                    w_pt.zero_()
+                    w_pt[roi_idx[:m]] = w[:m]
             if need_dinv:
                 _abi.check(lib.tal_pred_var_inv(_ptr(self.var[i]), _ptr(self.rho[i]), N,
                                                 _ptr(dinv), _stream()), "tal_pred_var_inv")
             pp0 = float(p0[i]) if p0 is not None else 0.0
-            _abi.check(lib.tal_colsum_lower(
-                rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(w),
-                _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt, _stream()),
-                "tal_colsum_lower")
+            if dense:
+                _abi.check(lib.tal_colsum_lower_dense(
+                    rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(roi_mask),
+                    _ptr(w), _ptr(w_pt), _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt,
+                    _stream()), "tal_colsum_lower_dense")
+            else:
+                _abi.check(lib.tal_colsum_lower(
+                    rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(w),
+                    _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt, _stream()),
+                    "tal_colsum_lower")
             self._sum(c)
             if rule == _abi.RULE_VTL:
                 _abi.check(lib.tal_roi_trace(_ptr(self.var[i]), _ptr(roi_idx), m, _ptr(tr),
