@@ -103,6 +103,12 @@ int tal_device_ok(void);
 int tal_gram_stationary(int kind, const double* X, long long n, const double* Y, long long m,
                         int d, double variance, double lengthscale, void* out, long long ld,
                         long long j0, long long n_rows, int dtype, void* stream);
+/* The covariance K(X, X) of a model in lower-block storage (see tal_rank1_update_lower): rows
+ * [j0, j0 + n_rows) of the Gram matrix over X itself, of which only the column tiles that reach into the
+ * kept part of a row (the columns below the end of its diagonal block) are computed and written; the rest of
+ * `out` is left untouched (nothing reads it before tal_sym_mirror rebuilds it).  j0 % 32 == 0. */
+int tal_gram_stationary_lower(int kind, const double* X, long long n, int d, double variance, double lengthscale,
+                              void* out, long long ld, long long j0, long long n_rows, int dtype, void* stream);
 
 /* ---- index lookup -------------------------------------------------------
  * Replaces get_indices (lib/utils.py:53-56): out[k] = argmin_j ||X[j]-A[k]||_2
@@ -187,7 +193,7 @@ int tal_sym_mirror(void* cov, long long cov_stride_q, long long ld, long long N,
  * Each entry sees the same sequence of rounded operations as p calls of
  * tal_rank1_update[_lower]: the result is bit-identical, the HBM traffic per
  * observation is divided by p (the pass stays HBM-bound up to p = 16).            */
-#define TAL_MAX_PENDING 16
+#define TAL_MAX_PENDING 32
 int tal_rankb_update(void* cov, long long cov_stride_q, long long ld, long long row0, long long n_loc,
                      long long N, int q, const void* K, const void* W, long long pend_stride, int p,
                      int lower, int dtype, void* stream);

@@ -35,10 +35,11 @@ def child():
             if only_ar and only_ar != arith:
                 continue
             gp = DeviceGP(N, 1, dtype=dtype, storage="lower", arith=arith)
+            gp.set_update_block(32)
             gp._cov.normal_()
             gp._Kp.normal_(); gp._Wp.normal_().mul_(1e-3)
             bytes_ = gp.update_bytes()
-            for p in ((int(only_p),) if only_p else (16, 8, 4)):
+            for p in ((int(only_p),) if only_p else (32, 16, 8, 4)):
                 def run():
                     _abi.check(gp.lib.tal_rankb_update(_ptr(gp._cov), gp.cov_stride_q, gp.ld, 0, N, N, 1, _ptr(gp._Kp),
                                                        _ptr(gp._Wp), gp.ld, p, 1, gp.dt_upd, _stream()))

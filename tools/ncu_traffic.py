@@ -51,7 +51,8 @@ def main():
              "dram_bytes_read": rd, "dram_bytes_write": wr,
              "dram_bytes": (rd or 0.0) + (wr or 0.0),
              "gpu_time_ms_under_ncu": mean("gpu__time_duration.sum"),
-             "dram_throughput_pct": mean("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+             "dram_throughput_pct": (mean("dram__bytes_read.sum.pct_of_peak_sustained_elapsed") or 0.0)
+                                    + (mean("dram__bytes_write.sum.pct_of_peak_sustained_elapsed") or 0.0),
              "sm_throughput_pct": mean("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
              "fp64_pipe_pct": mean("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
              "tensor_fp64_ops_pct": mean("sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed"),

@@ -431,12 +431,11 @@ potrf_diag_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ L
 //           registers, operands exchanged by shuffles;
 //       (b) panel  L_ip = S_ip inv(L_pp)^T  and (c) trailing update  S_ik -= L_ip L_kp^T  as 8 x 8 DMMA
 //           fragments straight out of shared memory (pitch 132 doubles: conflict-free fragment loads);
-//     and the 128 x 128 inverse is assembled by block doubling (16 -> 32 -> 64 -> 128),
-//       inv([[A, 0], [B, C]]) = [[inv A, 0], [-inv C B inv A, inv C]],
-//     two DMMA products per level.  The strictly lower part of the inverse lives TRANSPOSED in the unused
-//     upper triangle of the block's shared-memory copy, its diagonal in a side array.
+//     and the 128 x 128 inverse is assembled by blocked forward substitution (a DMMA product and a
+//     16-step solve per column for every 16-row block row).  The strictly lower part of the inverse lives
+//     TRANSPOSED in the unused upper triangle of the block's shared-memory copy, its diagonal in a side array.
 constexpr int D2_PA = NB + 4;   // pitch of the block copy
-constexpr int D2_PT = 64 + 4;   // pitch of the product scratch (64 x 64 per level in total)
+constexpr int D2_PT = 64 + 4;   // (the product scratch holds 64 x 68 doubles; used as 16 rows of pitch 116)
 constexpr int D2_PD = 16 + 4;   // pitch of the dense 16 x 16 inverse of the current diagonal block
 constexpr int D2_THREADS = 256;
 constexpr int D2_SMEM_BYTES = (NB * D2_PA + 64 * D2_PT + NB + 16 * D2_PD) * (int)sizeof(double);
@@ -498,10 +497,10 @@ __device__ __forceinline__ void d2_factor16(double* A, double* invd, double* Din
 __global__ void __launch_bounds__(D2_THREADS)
 potrf_diag_mma_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict__ Linv_all) {
   extern __shared__ __align__(16) double sm[];
-  constexpr int PA = D2_PA, PT = D2_PT, PD = D2_PD;
+  constexpr int PA = D2_PA, PD = D2_PD;
   double* A = sm;
   double* T = A + NB * PA;
-  double* invd = T + 64 * PT;
+  double* invd = T + 64 * D2_PT;
   double* Dinv = invd + NB;
   double* D = S + (i64)j * NB * lds + (i64)j * NB;
   double* Linv = Linv_all + (i64)j * NB * NB;
@@ -554,27 +553,38 @@ potrf_diag_mma_kernel(double* __restrict__ S, i64 lds, int j, double* __restrict
     }
     __syncthreads();
   }
-  // inverse by block doubling; pair pr at level s: blocks [b, b + s) and [b + s, b + 2 s), b = 2 s pr
-  for (int s = 16; s < NB; s *= 2) {
-    const int fr = s / 8, per_pair = fr * fr, total = (NB / (2 * s)) * per_pair;
-    for (int idx = warp; idx < total; idx += 8) {  // T = L21 inv(L11)
-      const int pr = idx / per_pair, w = idx % per_pair, mf = w / fr, nf = w % fr, b = pr * 2 * s;
+  // inverse by blocked forward substitution, one 16-row block row after the other:
+  //   X[bi, <bi] = -inv(L_bb) (L[bi, <bi] X[<bi, <bi])
+  // the product on DMMA fragments (X is lower triangular: k-steps below the column fragment are skipped),
+  // the 16 x 16 solve per column in one thread.  Row-wise this is what scalar forward substitution does, so
+  // L X - I stays at rounding level; that residual is what the panel (S_ij X^T) and the TRSM (X T_i) inherit.
+  // (A block-doubling inverse, inv([[A,0],[B,C]]) = [[inv A,0],[-inv C B inv A, inv C]], was measured first: its
+  // residual is amplified by |B inv A| -- 7.5e-10 on the RBF Gram blocks of BASELINE configs[0], enough to push a
+  // pivot of the NEXT block below zero against the 1e-10 jitter.)
+  constexpr int PR = 116;  // pitch of the 16-row product scratch (== 4 mod 16)
+  for (int bi = 1; bi < NB / 16; ++bi) {
+    const int r0 = bi * 16, ncf = r0 / 8;
+    for (int idx = warp; idx < 2 * ncf; idx += 8) {
+      const int mf = idx & 1, nf = idx >> 1;
       double u0 = 0.0, u1 = 0.0;
-      for (int ks = 0; ks < s / 4; ++ks)
-        dmma884(u0, u1, A[(b + s + mf * 8 + g) * PA + b + ks * 4 + t],
-                d2_inv_at(A, invd, b + ks * 4 + t, b + nf * 8 + g));
-      T[(pr * s + mf * 8 + g) * PT + nf * 8 + t * 2] = u0;
-      T[(pr * s + mf * 8 + g) * PT + nf * 8 + t * 2 + 1] = u1;
+      for (int ks = 2 * nf; ks < r0 / 4; ++ks)
+        dmma884(u0, u1, A[(r0 + mf * 8 + g) * PA + ks * 4 + t], d2_inv_at(A, invd, ks * 4 + t, nf * 8 + g));
+      T[(mf * 8 + g) * PR + nf * 8 + t * 2] = u0;
+      T[(mf * 8 + g) * PR + nf * 8 + t * 2 + 1] = u1;
     }
     __syncthreads();
-    for (int idx = warp; idx < total; idx += 8) {  // X21 = -inv(L22) T, stored transposed
-      const int pr = idx / per_pair, w = idx % per_pair, mf = w / fr, nf = w % fr, b = pr * 2 * s;
-      double u0 = 0.0, u1 = 0.0;
-      for (int ks = 0; ks < s / 4; ++ks)
-        dmma884(u0, u1, d2_inv_at(A, invd, b + s + mf * 8 + g, b + s + ks * 4 + t),
-                T[(pr * s + ks * 4 + t) * PT + nf * 8 + g]);
-      A[(b + nf * 8 + t * 2) * PA + b + s + mf * 8 + g] = -u0;
-      A[(b + nf * 8 + t * 2 + 1) * PA + b + s + mf * 8 + g] = -u1;
+    if ((int)threadIdx.x < r0) {
+      const int n = threadIdx.x;
+      double x[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        double sacc = -T[r * PR + n];
+#pragma unroll
+        for (int k = 0; k < r; ++k) sacc = fma(-A[(r0 + r) * PA + r0 + k], x[k], sacc);
+        x[r] = sacc * invd[r0 + r];
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) A[n * PA + r0 + r] = x[r];  // X[r0 + r][n], transposed
     }
     __syncthreads();
   }

@@ -53,11 +53,14 @@ constexpr int kGramRows = 32;  // rows of Y per CTA
 template <typename T, int KIND>
 __global__ void __launch_bounds__(256)
 gram_kernel(const double* __restrict__ X, i64 n, const double* __restrict__ Y, int d,
-            double variance, double lengthscale, T* __restrict__ out, i64 ld, i64 j0, i64 n_rows) {
+            double variance, double lengthscale, T* __restrict__ out, i64 ld, i64 j0, i64 n_rows, i64 sym_block) {
   typedef typename Vec16<T>::type V;
   constexpr int VN = Vec16<T>::n;
   __shared__ double ys[kGramRows][kMaxD];
   const i64 jr0 = (i64)blockIdx.y * kGramRows;  // first local row of this CTA
+  // lower-block storage: the rows of a CTA share one diagonal block (kGramRows == the block size, j0 aligned);
+  // column tiles beyond its end are never read by anyone and are not written (half of the one-off build)
+  if (sym_block > 0 && (i64)blockIdx.x * 256 * VN >= ((j0 + jr0) / sym_block + 1) * sym_block) return;
   const int nr = (int)min((i64)kGramRows, n_rows - jr0);
   for (int e = threadIdx.x; e < nr * d; e += blockDim.x)
     ys[e / d][e % d] = Y[(j0 + jr0 + e / d) * d + e % d];
@@ -84,11 +87,11 @@ gram_kernel(const double* __restrict__ X, i64 n, const double* __restrict__ Y, i
 
 template <typename T>
 static void launch_gram(int kind, const double* X, i64 n, const double* Y, int d, double variance,
-                        double lengthscale, T* out, i64 ld, i64 j0, i64 n_rows, cudaStream_t st) {
+                        double lengthscale, T* out, i64 ld, i64 j0, i64 n_rows, cudaStream_t st, i64 sym_block = 0) {
   constexpr int VN = Vec16<T>::n;
   dim3 grid((unsigned)((ld + 256 * VN - 1) / (256 * VN)), (unsigned)((n_rows + kGramRows - 1) / kGramRows));
 #define TAL_GRAM(K) \
-  gram_kernel<T, K><<<grid, 256, 0, st>>>(X, n, Y, d, variance, lengthscale, out, ld, j0, n_rows)
+  gram_kernel<T, K><<<grid, 256, 0, st>>>(X, n, Y, d, variance, lengthscale, out, ld, j0, n_rows, sym_block)
   switch (kind) {
     case TAL_KERNEL_GAUSSIAN: TAL_GRAM(TAL_KERNEL_GAUSSIAN); break;
     case TAL_KERNEL_LAPLACE: TAL_GRAM(TAL_KERNEL_LAPLACE); break;
@@ -154,6 +157,26 @@ int tal_gram_stationary(int kind, const double* X, long long n, const double* Y,
     launch_gram<float>(kind, X, n, Y, d, variance, lengthscale, (float*)out, ld, j0, n_rows,
                        as_stream(stream));
   TAL_LAUNCH_CHECK("tal_gram_stationary");
+  return TAL_OK;
+}
+
+/* K(X, X) rows [j0, j0 + n_rows) in lower-block storage: only the column tiles that reach into the kept part
+ * of a row block (columns below the end of its diagonal block) are computed and written. */
+int tal_gram_stationary_lower(int kind, const double* X, long long n, int d, double variance, double lengthscale,
+                              void* out, long long ld, long long j0, long long n_rows, int dtype, void* stream) {
+  TAL_ARG(X && out && n >= 1 && d >= 1 && d <= kMaxD);
+  TAL_ARG(kind >= TAL_KERNEL_GAUSSIAN && kind <= TAL_KERNEL_LINEAR);
+  TAL_ARG(ld >= n && ld % 32 == 0 && j0 >= 0 && j0 % kGramRows == 0 && n_rows >= 0 && j0 + n_rows <= n);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  static_assert(kGramRows == 32, "a CTA's rows must share one diagonal block");
+  if (n_rows == 0) return TAL_OK;
+  TAL_ARG((n_rows + kGramRows - 1) / kGramRows <= 65535);
+  const i64 blk = tal_sym_block(dtype);
+  if (dtype == TAL_F64)
+    launch_gram<double>(kind, X, n, X, d, variance, lengthscale, (double*)out, ld, j0, n_rows, as_stream(stream), blk);
+  else
+    launch_gram<float>(kind, X, n, X, d, variance, lengthscale, (float*)out, ld, j0, n_rows, as_stream(stream), blk);
+  TAL_LAUNCH_CHECK("tal_gram_stationary_lower");
   return TAL_OK;
 }
 

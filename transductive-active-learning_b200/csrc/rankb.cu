@@ -129,7 +129,7 @@ __device__ __forceinline__ void rb_cp_async_wait() {
 }
 
 template <typename T, int P, bool FMA, int ROWS, int D>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (P > 16 ? 1 : 2))  // (32 w-vectors = 128 registers: one CTA per SM)
 rankb_async_kernel(T* __restrict__ cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, const T* __restrict__ K,
                    const T* __restrict__ W, i64 pend_stride, int p, i64 sym_block) {
   typedef typename VecB<T>::type V;
@@ -267,15 +267,20 @@ static int launch_rankb(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int q
   } while (0)
   int v = rankb_variant();
   if (v < 0) v = P >= 16 ? (FMA ? 6 : 5) : 0;
-  if (v == 5) TAL_RBA(128, 8);
-  else if (v == 6) TAL_RBA(128, 16);
-  else if (v == 7) TAL_RBA(256, 16);
-  else if (v == 8) TAL_RBA(128, 24);
-  else if (v == 1) TAL_RB(8, 128);
-  else if (v == 2) TAL_RB(UD, 256);
-  else if (v == 3) TAL_RB(8, 256);
-  else if (v == 4) TAL_RB(UD, 32);
-  else TAL_RB(UD, 128);
+  if constexpr (P > 16) {  // 32 updates per pass: ring variants only (the w-vectors alone fill the register file)
+    if (v == 8) TAL_RBA(128, 24);
+    else TAL_RBA(128, 16);
+  } else {
+    if (v == 5) TAL_RBA(128, 8);
+    else if (v == 6) TAL_RBA(128, 16);
+    else if (v == 7) TAL_RBA(256, 16);
+    else if (v == 8) TAL_RBA(128, 24);
+    else if (v == 1) TAL_RB(8, 128);
+    else if (v == 2) TAL_RB(UD, 256);
+    else if (v == 3) TAL_RB(8, 256);
+    else if (v == 4) TAL_RB(UD, 32);
+    else TAL_RB(UD, 128);
+  }
 #undef TAL_RB
 #undef TAL_RBA
   return 0;
@@ -287,7 +292,8 @@ static int rankb_dispatch(T* cov, i64 stride_q, i64 ld, i64 row0, i64 n_loc, int
   if (p <= 2) return launch_rankb<T, 2, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
   if (p <= 4) return launch_rankb<T, 4, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
   if (p <= 8) return launch_rankb<T, 8, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
-  return launch_rankb<T, 16, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
+  if (p <= 16) return launch_rankb<T, 16, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
+  return launch_rankb<T, 32, FMA>(cov, stride_q, ld, row0, n_loc, q, K, W, pend_stride, p, sym_block, st);
 }
 
 }  // namespace tal

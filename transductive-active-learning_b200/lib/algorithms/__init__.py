@@ -61,7 +61,8 @@ class DiscreteGreedyAlgorithm(GreedyAlgorithm):
         idx = self.model._argmax_index(F, self.sample_mask())  # masks F in place (:80-81)
         F = self.model._gp.gather_candidates(F)
         X = self.model.domain[idx: idx + 1]
-        y = f.observe(X)
+        # (a black box that declares `host_input` gets the row of the model's host copy of the domain)
+        y = f.observe(torch.from_numpy(self.model.domain_host()[idx: idx + 1]) if getattr(f, "host_input", False) else X)
         if update_model:
             self.model.step(X=X, y=y)
         if not isinstance(y, torch.Tensor):  # a host black box: keep its observation on the host

@@ -33,27 +33,35 @@ class ITL(DirectedDiscreteGreedyAlgorithm):
             roi = self.roi
             if st["key"] is roi and self._incremental(roi) and not model.safe_set_is_subset_of(A=roi):
                 rec = gp.ctx_select(model.first_constraint, model._safe_override(), self.sample_mask())
-                idx = model._check_argmax(gp.read_result(rec))
-                F = gp._scratch("ctx_F", (gp.n_cand,)).clone()  # (the update below overwrites it with the next scores)
-                if gp.sharded and self.gather_F:
-                    F = gp.gather_candidates(F)
                 # a device-resident black box (a lookup: no host round trip) gets the whole update as one fused
                 # call; any other black box is asked for y WHILE the device does everything that does not need
-                # it (observed row, weights, variances, conditioning pass: ~all of the step), then the means /
-                # bounds and the selection of the next candidate are enqueued behind it
-                if getattr(f, "host_input", False):
-                    X = torch.from_numpy(model.domain_host()[idx: idx + 1])
-                else:
-                    X = model.domain[idx: idx + 1]
+                # it (observed row, weights, variances, conditioning pass: ~all of the step): that part is
+                # enqueued straight after the record has been read -- its index is taken from the record on the
+                # device, and a failed arg-max is a no-op there -- then the means / bounds and the selection of
+                # the next candidate are enqueued behind it
                 if getattr(f, "device_resident", False):
+                    idx = model._check_argmax(gp.read_result(rec))
+                    F = gp._scratch("ctx_F", (gp.n_cand,)).clone()  # (the update overwrites it with the next scores)
+                    X = model.domain[idx: idx + 1]
                     y = f.observe(X)
                     model._step_index(rec[0:1], y, auto_select=True)
                 else:
-                    model._step_index_begin(rec[0:1])
+                    c, stream = gp.ctx_observe_prepare(model._beta_now())  # beta at the OLD t (:366-368)
+                    idx_ptr = rec.data_ptr()
+                    res = gp.read_result(rec)                 # the one host synchronisation of the step
+                    gp.ctx_observe_fire(c, stream, idx_ptr)   # device busy again
+                    idx = model._check_argmax(res)
+                    F = gp._scratch("ctx_F", (gp.n_cand,)).clone()  # (still this step's scores: rewritten by the select below)
+                    if getattr(f, "host_input", False):
+                        X = torch.from_numpy(model.domain_host()[idx: idx + 1])
+                    else:
+                        X = model.domain[idx: idx + 1]
                     y = f.observe(X)
                     model._step_index_end(rec[0:1], y)
                     if gp._cond is not None and gp._cond["valid"]:
                         gp.ctx_select(model.first_constraint, model._safe_override(), self.sample_mask())
+                if gp.sharded and self.gather_F:
+                    F = gp.gather_candidates(F)
                 if not isinstance(y, torch.Tensor):
                     import numpy as np
                     y = torch.as_tensor(np.asarray(y, dtype=np.float64))

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtal_b200.so")
 TAL_OK = 0
 TAL_MAX_Q = 16
 TAL_PEER_MAX = 16
-TAL_MAX_PENDING = 16
+TAL_MAX_PENDING = 32
 TAL_PEER_HANDLE_BYTES = 64
 F64, F32 = 0, 1
 KERNEL_GAUSSIAN, KERNEL_LAPLACE, KERNEL_MATERN32, KERNEL_MATERN52, KERNEL_LINEAR = range(5)
@@ -80,6 +80,7 @@ SIGNATURES = {
     "tal_reset_launch_count": (None, []),
     "tal_device_ok": (_i, []),
     "tal_gram_stationary": (_i, [_i, _p, _ll, _p, _ll, _i, _d, _d, _p, _ll, _ll, _ll, _i, _p]),
+    "tal_gram_stationary_lower": (_i, [_i, _p, _ll, _i, _d, _d, _p, _ll, _ll, _ll, _i, _p]),
     "tal_nearest_index": (_i, [_p, _ll, _p, _ll, _i, _p, _p]),
     "tal_extract_row": (_i, [_p, _ll, _ll, _ll, _ll, _ll, _i, _p, _ll, _p, _p, _p, _i, _p]),
     "tal_step_vectors": (_i, [_p, _p, _ll, _i, _p, _ll, _p, _ll, _i, _p, C.POINTER(_d), _p,

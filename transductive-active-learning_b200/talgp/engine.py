@@ -327,6 +327,23 @@ class DeviceGP:
             _abi.check(rc, "tal_ctx_observe")
         self._ctx_done(c)
 
+    def ctx_observe_prepare(self, beta: Sequence[float]):
+        """First half of a value-less `ctx_observe` (see ITL._step): everything the host can do BEFORE it knows
+        the selection -- the context with its pointers, beta, the stream handle."""
+        c = self._ctx_get()
+        for i in range(self.q):
+            c.beta[i] = float(beta[i])
+        c.auto_select = 0
+        return c, _stream()
+
+    def ctx_observe_fire(self, c, stream, idx_ptr: int) -> None:
+        """Second half: enqueue the y-independent part of the observation at the index stored at device
+        address idx_ptr (the arg-max record): one ctypes call, three launches."""
+        rc = self.lib.tal_ctx_observe(C.byref(c), C.c_void_p(idx_ptr), 0, None, 1, 0, stream)
+        if rc != _abi.TAL_CTX_REBASE:
+            _abi.check(rc, "tal_ctx_observe")
+        self._ctx_done(c)
+
     def ctx_observe_y(self, idx_dev, idx_host, y_dev: torch.Tensor, y_stride: int, y_gather: bool) -> None:
         c = self._ctx
         _abi.check(self.lib.tal_ctx_observe_y(C.byref(c), _ptr(idx_dev), int(idx_host), _ptr(y_dev), int(y_stride),
@@ -459,12 +476,17 @@ class DeviceGP:
         n, d = domain.shape
         assert n == self.N
         self.flush()
-        if self.q == 1:
-            self._upper_stale = False  # (with several GPs the flag keeps covering the other ones)
-        _abi.check(self.lib.tal_gram_stationary(
-            kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
-            _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
-            "tal_gram_stationary")
+        if self.lower:  # only the kept blocks are built; the mirrored ones on demand (tal_sym_mirror)
+            self._upper_stale = True
+            _abi.check(self.lib.tal_gram_stationary_lower(
+                kind, _ptr(domain), n, d, float(variance), float(lengthscale),
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
+                "tal_gram_stationary_lower")
+        else:
+            _abi.check(self.lib.tal_gram_stationary(
+                kind, _ptr(domain), n, _ptr(domain), n, d, float(variance), float(lengthscale),
+                _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.dt, _stream()),
+                "tal_gram_stationary")
         # diagonal of a stationary kernel: k(x, x), evaluated by the same kernel
         # on a one-row problem per point is wasteful; the diagonal entries of
         # the shard are copied instead and completed by the caller when sharded.
