@@ -529,6 +529,15 @@ def run_itl(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, war
         dist.barrier()
     total_ms = float(_max_over_ranks(t0.elapsed_time(t1), dev, world)[0])
     launches = int(lib.tal_launch_count())
+    breakdown = None
+    if os.environ.get("TAL_BREAKDOWN") and ctx is not None:
+        bd, nbd = (C.c_double * 6)(), C.c_longlong(0)
+        _abi.check(lib.tal_ctx_breakdown(bd, C.byref(nbd)))
+        bdv = _max_over_ranks([float(x) for x in bd], dev, world)
+        breakdown = dict(zip(("peer_push_us", "fused_observe_us", "fused_partial_us", "fused_finish_us",
+                              "pass_amortised_us", "gap_to_next_step_us"), [float(x) for x in bdv]), steps=int(nbd.value),
+                         note="CUDA events between the launches of tal_ctx_observe (max over ranks per phase); "
+                              "the events themselves cost ~1-2 us per phase")
     if ctx is not None:
         ms_buf, up_buf, n_buf = (C.c_double * 64)(), (C.c_longlong * 64)(), C.c_longlong(0)
         _abi.check(lib.tal_ctx_timing_read(C.byref(ctx), ms_buf, up_buf, C.byref(n_buf), stream))
@@ -637,7 +646,7 @@ def run_itl(args, w, dev, world, rank, comm, lib, hbm_peak, peak_src, steps, war
     line = {
         "value": steps / (total_ms / 1e3), "ms_per_step": total_ms / steps, "steps": steps,
         "config": dict(workload_config(args, w, world), **({"exchange": exchange} if exchange else {})),
-        "gpu_launches": launches, "invariants": invariants,
+        "gpu_launches": launches, "invariants": invariants, **({"breakdown_us": breakdown} if breakdown else {}),
         "roofline": roofs[0] if roofs else None,
         "roofline_other_instantiations": roofs[1:],
         "kernels": [],

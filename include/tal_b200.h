@@ -562,6 +562,10 @@ typedef struct tal_step_ctx {
   const unsigned char *sel_safe, *sel_sample; long long sel_fc;  /* masks the selection was made under */
   void* fz_scratch;                  /* tal_fused_scratch_bytes(q, ncols, n_split) */
 } tal_step_ctx;
+/* diagnostic (TAL_BREAKDOWN=1): mean microseconds per phase of the recorded fused steps -- [0] peer push + record
+ * combine, [1] fused_observe (+ row wait), [2] fused_partial, [3] fused_finish (+ arg-max, publish), [4] covariance
+ * pass (amortised over the steps), [5] gap to the next step; *n_host = steps seen.  Synchronises the device. */
+int tal_ctx_breakdown(double* out_us_host, long long* n_host);
 long long tal_step_ctx_bytes(void);
 long long tal_fused_scratch_bytes(int q, long long ncols, int n_split);
 int tal_ctx_select(tal_step_ctx* ctx, void* stream);

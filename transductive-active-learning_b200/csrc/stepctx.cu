@@ -16,6 +16,7 @@
 //   tal_ctx_step     both, the observation taken from a device table
 #include "fused.cuh"
 #include "peer.cuh"
+#include <cstdlib>
 
 using namespace tal;
 
@@ -32,6 +33,27 @@ static void ev_record(tal_step_ctx* c, bool start, void* stream, long long updat
     c->ev_updates[c->n_ev] = updates;  // updates applied by the pass these events bracket
     c->n_ev += 1;
   }
+}
+
+// Per-phase breakdown of a fused step (diagnostic, TAL_BREAKDOWN=1): CUDA events between the launches of
+// tal_ctx_observe for up to 256 steps, read by tal_ctx_breakdown (bench.py prints them as `breakdown_us`).
+static int g_bd = -1;
+static constexpr int kBdSteps = 256, kBdMarks = 6;
+static cudaEvent_t g_bd_ev[kBdSteps][kBdMarks];
+static bool g_bd_has[kBdSteps][kBdMarks];
+static int g_bd_n = 0;
+static bool bd_on() {
+  if (g_bd < 0) {
+    const char* e = getenv("TAL_BREAKDOWN");
+    g_bd = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_bd == 1 && g_bd_n < kBdSteps;
+}
+static void bd_mark(int k, cudaStream_t st) {
+  if (!bd_on()) return;
+  if (!g_bd_ev[g_bd_n][k]) cudaEventCreate(&g_bd_ev[g_bd_n][k]);
+  cudaEventRecord(g_bd_ev[g_bd_n][k], st);
+  g_bd_has[g_bd_n][k] = true;
 }
 
 static inline int upd_dtype(const tal_step_ctx* c) { return (int)c->dtype | (c->arith ? TAL_ARITH_FMA : 0); }
@@ -125,6 +147,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
   }
   const bool combine_in_push = c->G > 1 && c->sel_state == 1;
   bool scal_ok = own && c->scal_ok != 0;
+  bd_mark(0, st);
   if (c->G > 1) {
     rc = peer_push_row_impl(c->mailboxes, (int)c->G, (int)c->rank, c->bounds, c->cov, c->cov_stride_q, c->ld, c->N, q,
                             (int)c->lower, idx_dev, idx_host, c->kbuf_off, cond ? c->Wb : nullptr,
@@ -142,6 +165,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
     rc = fused_stash_mean(c->mean, c->N, q, idx_dev, idx_host, c->scal, st);
     if (rc != TAL_OK) return rc;
   }
+  bd_mark(1, st);
   const long long s = dtype == TAL_F64 ? 8 : 4;
   FusedObs o;
   o.cov = c->cov; o.stride_q = c->cov_stride_q; o.ld = c->ld; o.N = c->N;
@@ -160,6 +184,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
   o.mailbox = c->G > 1 ? c->mailbox : nullptr; o.G = (int)c->G; o.wait = cond ? 1 : 0;
   rc = fused_observe(o, q, upd_dtype(c), st);
   if (rc != TAL_OK) return rc;
+  bd_mark(2, st);
   c->scal_ok = 0;
   c->sel_state = 0;
   if (cond) {
@@ -170,6 +195,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
                        c->G > 1 ? c->pcol_peer : nullptr, c->pcol_stride, c->ncols, part, colsq, (int)c->n_split, q,
                        st);
     if (rc != TAL_OK) return rc;
+    bd_mark(3, st);
     const bool select = c->auto_select != 0 && y_dev != nullptr;  // (l, u are final only once y has been applied)
     FusedFin f;
     f.Wb = c->Wb; f.wb_stride_q = c->cap_rows * c->ldw; f.ldw = c->ldw; f.rows = c->rows; f.ncols = c->ncols;
@@ -182,6 +208,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
     f.boxes = c->mailboxes; f.G = (int)c->G; f.rank = (int)c->rank;
     rc = fused_finish(f, dtype, st);
     if (rc != TAL_OK) return rc;
+    bd_mark(4, st);
     c->rows += 2;
     if (select) {
       c->sel_state = c->G > 1 ? 1 : 2;
@@ -197,6 +224,8 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
       rc = ctx_flush(c, stream);
       if (rc != TAL_OK) return rc;
     }
+    bd_mark(5, st);
+    if (bd_on()) g_bd_n += 1;
     return rebase ? TAL_CTX_REBASE : TAL_OK;
   }
   c->passes += 1;
@@ -232,6 +261,42 @@ int tal_ctx_step(tal_step_ctx* c, void* stream) {
 }
 
 long long tal_step_ctx_bytes(void) { return (long long)sizeof(tal_step_ctx); }
+
+/* Diagnostic (TAL_BREAKDOWN=1): mean microseconds of the phases of the last recorded fused steps --
+ * out_us[0] peer push (+ record combine), [1] fused_observe (+ row wait), [2] fused_partial, [3] fused_finish
+ * (+ arg-max + publish), [4] covariance pass (amortised), [5] gap between consecutive steps; *n = steps seen.
+ * Synchronises the device and resets the recording. */
+int tal_ctx_breakdown(double* out_us_host, long long* n_host) {
+  TAL_ARG(out_us_host && n_host);
+  TAL_CUDA(cudaDeviceSynchronize());
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long long cnt = 0, gaps = 0;
+  for (int s = 0; s < g_bd_n; ++s) {
+    bool all = true;
+    for (int k = 0; k < kBdMarks; ++k) all = all && g_bd_has[s][k];
+    if (!all) continue;
+    cnt += 1;
+    const int a[5] = {0, 1, 2, 3, 4}, b[5] = {1, 2, 3, 4, 5};
+    for (int k = 0; k < 5; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_bd_ev[s][a[k]], g_bd_ev[s][b[k]]);
+      acc[k] += ms * 1e3;
+    }
+    if (s + 1 < g_bd_n && g_bd_has[s + 1][0]) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_bd_ev[s][5], g_bd_ev[s + 1][0]);
+      acc[5] += ms * 1e3;
+      gaps += 1;
+    }
+  }
+  for (int k = 0; k < 5; ++k) out_us_host[k] = cnt ? acc[k] / cnt : 0.0;
+  out_us_host[5] = gaps ? acc[5] / gaps : 0.0;
+  *n_host = cnt;
+  for (int s = 0; s < g_bd_n; ++s)
+    for (int k = 0; k < kBdMarks; ++k) g_bd_has[s][k] = false;
+  g_bd_n = 0;
+  return TAL_OK;
+}
 
 int tal_ctx_timing_begin(tal_step_ctx* c) {
   TAL_ARG(c);

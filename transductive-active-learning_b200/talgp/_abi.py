@@ -146,6 +146,7 @@ SIGNATURES = {
     "tal_sym_mirror": (_i, [_p, _ll, _ll, _ll, _i, _i, _p]),
     "tal_peer_error": (_i, [_p, C.POINTER(_i), _p]),
     "tal_step_ctx_bytes": (_ll, []),
+    "tal_ctx_breakdown": (_i, [C.POINTER(_d), C.POINTER(_ll)]),
     "tal_ctx_select": (_i, [_p, _p]),
     "tal_ctx_observe": (_i, [_p, _p, _ll, _p, _ll, _i, _p]),
     "tal_ctx_step": (_i, [_p, _p]),
