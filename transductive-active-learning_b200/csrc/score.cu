@@ -7,6 +7,7 @@
 // cov[a, x] for a in the ROI through nested vmaps; here the ROI rows are
 // streamed once (m*N*sizeof(T) bytes) and reduced per column.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace tal {
 
@@ -136,6 +137,77 @@ colsum_cols_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, const i64* __re
   }
   acc = warp_sum(acc);
   if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
+}
+
+// Kept-part row reduce for an ROI that covers a large part of the domain (lower-block storage): rows are walked
+// directly (a = j, masked by the ROI's byte mask) instead of through the index list, the end of a row's kept part
+// is a shift (the block size is 32), and a thread starts at the first row that keeps its column.  The gather form
+// above spends ~100 integer instructions per 16-byte load on the index, a 64-bit division and the bounds and runs
+// at 0.35 of the copy peak when m ~ N; this one streams.  grid (column tiles, row splits); row split s covers rows
+// [s * per, (s + 1) * per); UNROLL rows in flight per thread.
+template <typename T, int RULE, bool HAS_W, int VPT>
+__global__ void __launch_bounds__(256)
+colsum_rows_dense_kernel(const T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N,
+                         const unsigned char* __restrict__ roi_mask, const double* __restrict__ w_pt,
+                         const double* __restrict__ dinv, double p0, double p1, double* __restrict__ part, i64 per) {
+  // a CTA covers VPT * 256 consecutive 16-byte vectors of a row (VPT * 4 KB contiguous): thread t owns vectors
+  // t, t + 256, ...; UNROLL rows in flight
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
+  constexpr int UNROLL = VPT == 1 ? 8 : 2;
+  const i64 tile0 = (i64)blockIdx.x * 256 * VPT * VN;
+  double acc[VPT][VN], di[VPT][VN];
+  i64 colv[VPT];
+  i64 lo = 0x7fffffffffffffffLL;
+#pragma unroll
+  for (int p = 0; p < VPT; ++p) {
+    colv[p] = tile0 + ((i64)p * 256 + threadIdx.x) * VN;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      acc[p][e] = 0.0;
+      di[p][e] = (dinv && colv[p] + e < N) ? dinv[colv[p] + e] : 0.0;
+    }
+    if (colv[p] < ld && colv[p] < lo) lo = colv[p];
+  }
+  if (lo >= ld) return;
+  // local rows [j0, j1) of this split; row a = row0 + j keeps column c iff a >= (c / 32) * 32
+  i64 j0 = (i64)blockIdx.y * per, j1 = j0 + per;
+  if (j1 > n_loc) j1 = n_loc;
+  const i64 first = ((lo >> 5) << 5) - row0;  // (the thread's lowest column: later ones start later, checked per row)
+  if (first > j0) j0 = first;
+  for (i64 j = j0; j < j1; j += UNROLL) {
+    V c[UNROLL][VPT];
+    bool ok[UNROLL][VPT];
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      const bool row_ok = j + t < j1 && roi_mask[row0 + j + t] != 0;
+      const i64 a32 = ((row0 + j + t) >> 5) << 5;
+#pragma unroll
+      for (int p = 0; p < VPT; ++p) {
+        ok[t][p] = row_ok && colv[p] < ld && colv[p] < a32 + 32;
+        if (ok[t][p]) c[t][p] = ld_stream(reinterpret_cast<const V*>(cov + (j + t) * ld + colv[p]));
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < UNROLL; ++t) {
+      const double wa = (HAS_W && j + t < j1) ? w_pt[row0 + j + t] : 1.0;
+#pragma unroll
+      for (int p = 0; p < VPT; ++p) {
+        if (ok[t][p]) {
+          T e[VN];
+          memcpy(e, &c[t][p], sizeof(V));
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[p][k] += elem<RULE>((double)e[k], wa, di[p][k], p0, p1);
+        }
+      }
+    }
+  }
+  double* o = part + (i64)blockIdx.y * N;
+#pragma unroll
+  for (int p = 0; p < VPT; ++p)
+#pragma unroll
+    for (int e = 0; e < VN; ++e)
+      if (colv[p] + e < N) o[colv[p] + e] = acc[p][e];
 }
 
 // The same mirrored sums when the ROI is a large part of the domain (potential-maximiser ROIs of the
@@ -383,12 +455,54 @@ int tal_colsum_lower_dense(int rule, const void* cov, long long ld, long long ro
                            const double* row_weight, const double* w_pt, const double* dinv, double p0,
                            double p1, double* part, int n_split, double* c_out, int dtype, void* stream) {
   TAL_ARG(roi_mask && ((row_weight == nullptr) == (w_pt == nullptr)));
+  TAL_ARG(cov && part && c_out && n_split >= 1 && n_split <= 65535 && ld % 32 == 0 && ld >= N);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
+  TAL_ARG(tal_sym_block(dtype) == 32);  // (the kernels below shift)
+  (void)roi_idx; (void)m;
   const i64 blk = tal_sym_block(dtype);
-  int rc = colsum_rows_impl(rule, cov, ld, row0, n_loc, N, roi_idx, m, row_weight, dinv, p0, p1, part,
-                            n_split, c_out, dtype, stream, blk);
-  if (rc != TAL_OK) return rc;
-  if (n_loc == 0) return TAL_OK;
   cudaStream_t st = as_stream(stream);
+  {  // kept part of the ROI rows this shard holds: part[s][x], s < n_split, then a fixed-order sum
+    const i64 per = (n_loc + n_split - 1) / n_split > 0 ? (n_loc + n_split - 1) / n_split : 1;
+    const i64 vn = dtype == TAL_F64 ? 2 : 4;
+    static int vpt = -1;  // 1 (default): 4 KB of a row per CTA, 1.27 ms per fp32 matrix at C4 = the copy peak;
+                          // TAL_ROWS_DENSE_VPT=4: 16 KB per CTA (measured 1.69 ms: fewer, fatter CTAs)
+    if (vpt < 0) {
+      const char* e = getenv("TAL_ROWS_DENSE_VPT");
+      vpt = (e && atoi(e) == 4) ? 4 : 1;
+    }
+    dim3 grid((unsigned)((ld + 256 * vn * vpt - 1) / (256 * vn * vpt)), (unsigned)n_split);
+    double* dst = n_split == 1 ? c_out : part;
+#define TAL_RD2(T, R, W, P)                                                                                    \
+  colsum_rows_dense_kernel<T, R, W, P><<<grid, 256, 0, st>>>((const T*)cov, ld, row0, n_loc, N, roi_mask, w_pt, \
+                                                              dinv, p0, p1, dst, per)
+#define TAL_RD(T, R)                                                                                         \
+  do {                                                                                                       \
+    if (vpt == 1) { if (w_pt) TAL_RD2(T, R, true, 1); else TAL_RD2(T, R, false, 1); }                        \
+    else { if (w_pt) TAL_RD2(T, R, true, 4); else TAL_RD2(T, R, false, 4); }                                 \
+  } while (0)
+    if (dtype == TAL_F64) {
+      switch (rule) {
+        case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_RD(double, TAL_RULE_VTL); break;
+        case TAL_RULE_MMITL: TAL_RD(double, TAL_RULE_MMITL); break;
+        default: TAL_RD(double, TAL_RULE_TRUVAR); break;
+      }
+    } else {
+      switch (rule) {
+        case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_RD(float, TAL_RULE_VTL); break;
+        case TAL_RULE_MMITL: TAL_RD(float, TAL_RULE_MMITL); break;
+        default: TAL_RD(float, TAL_RULE_TRUVAR); break;
+      }
+    }
+#undef TAL_RD2
+#undef TAL_RD
+    TAL_LAUNCH_CHECK("tal_colsum_lower_dense/rows");
+    if (n_split > 1) {
+      sum_parts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(part, n_split, N, c_out);
+      TAL_LAUNCH_CHECK("tal_colsum_lower_dense/sum_parts");
+    }
+  }
+  if (n_loc == 0) return TAL_OK;
   const unsigned grid = (unsigned)((n_loc + 7) / 8);
   const double* dv = dinv ? dinv + row0 : nullptr;
 #define TAL_CD(T, R)                                                                                         \

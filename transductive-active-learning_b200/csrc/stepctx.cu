@@ -17,6 +17,7 @@
 #include "fused.cuh"
 #include "peer.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 using namespace tal;
 
@@ -269,28 +270,34 @@ long long tal_step_ctx_bytes(void) { return (long long)sizeof(tal_step_ctx); }
 int tal_ctx_breakdown(double* out_us_host, long long* n_host) {
   TAL_ARG(out_us_host && n_host);
   TAL_CUDA(cudaDeviceSynchronize());
-  double acc[6] = {0, 0, 0, 0, 0, 0};
+  static double v[6][kBdSteps];
   long long cnt = 0, gaps = 0;
+  double pass_sum = 0.0;
   for (int s = 0; s < g_bd_n; ++s) {
     bool all = true;
     for (int k = 0; k < kBdMarks; ++k) all = all && g_bd_has[s][k];
     if (!all) continue;
-    cnt += 1;
-    const int a[5] = {0, 1, 2, 3, 4}, b[5] = {1, 2, 3, 4, 5};
     for (int k = 0; k < 5; ++k) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, g_bd_ev[s][a[k]], g_bd_ev[s][b[k]]);
-      acc[k] += ms * 1e3;
+      cudaEventElapsedTime(&ms, g_bd_ev[s][k], g_bd_ev[s][k + 1]);
+      v[k][cnt] = ms * 1e3;
     }
+    pass_sum += v[4][cnt];
+    cnt += 1;
     if (s + 1 < g_bd_n && g_bd_has[s + 1][0]) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, g_bd_ev[s][5], g_bd_ev[s + 1][0]);
-      acc[5] += ms * 1e3;
-      gaps += 1;
+      v[5][gaps++] = ms * 1e3;
     }
   }
-  for (int k = 0; k < 5; ++k) out_us_host[k] = cnt ? acc[k] / cnt : 0.0;
-  out_us_host[5] = gaps ? acc[5] / gaps : 0.0;
+  // medians (a few steps sit next to host-side set-up work); the pass is amortised: its mean
+  for (int k = 0; k < 6; ++k) {
+    const long long n = k == 5 ? gaps : cnt;
+    if (n == 0) { out_us_host[k] = 0.0; continue; }
+    std::sort(v[k], v[k] + n);
+    out_us_host[k] = v[k][n / 2];
+  }
+  out_us_host[4] = cnt ? pass_sum / cnt : 0.0;
   *n_host = cnt;
   for (int s = 0; s < g_bd_n; ++s)
     for (int k = 0; k < kBdMarks; ++k) g_bd_has[s][k] = false;

@@ -765,11 +765,12 @@ class DeviceGP:
         need_dinv = rule in (_abi.RULE_MMITL, _abi.RULE_TRUVAR)
         w = self._scratch("score_w", (max(m, 1),)) if need_w else None
         dinv = self._scratch("score_dinv", (N,)) if need_dinv else None
-        n_split = self._n_split(m)
-        part = self._scratch("score_part", (n_split, N))
         # an ROI that covers a large part of the domain (m ~ N for the potential maximisers of the Safe-BO
-        # configurations): stream + mask the mirrored part instead of gathering it entry by entry
+        # configurations): stream + mask the rows instead of gathering them entry by entry; row splits of ~256
+        # rows (the triangular kept part makes the CTAs unequal: many small ones keep the tail short)
         dense = 4 * m >= N
+        n_split = int(max(1, min(1024, -(-self.n_loc // 256)))) if dense else self._n_split(m)
+        part = self._scratch("score_part", (n_split, N))
         if dense:
             if roi_mask is None or roi_mask.numel() != N:
                 roi_mask = torch.zeros((N,), dtype=torch.uint8, device=self.device)
