@@ -293,6 +293,17 @@ int tal_colsum_lower_dense(int rule, const void* cov, long long ld, long long ro
                            long long N, const long long* roi_idx, long long m, const unsigned char* roi_mask,
                            const double* row_weight, const double* w_pt, const double* dinv, double p0,
                            double p1, double* part, int n_split, double* c_out, int dtype, void* stream);
+/* ... and fused with the posterior update that precedes it (a VTL-type step flushes its ONE pending rank-1 update
+ * before it scores: lib/model/marginal.py:350-368 followed by lib/algorithms/vtl.py:21-41): one pass applies
+ * cov[a][b] <- cov[a][b] - k[a] w[b] (the rounded operation of tal_rank1_update_lower, `dtype` may carry
+ * TAL_ARITH_FMA) to every kept entry of ONE GP and accumulates both halves of tal_colsum_lower_dense from the updated
+ * values: 2 transfers of the matrix per step instead of 4.  kvec, wvec: [ld] of the cov dtype (the pending slot of this
+ * GP); rowpart: tal_update_colsum_scratch_bytes(ld, n_loc, dtype) bytes; part: [n_split][N]. */
+long long tal_update_colsum_scratch_bytes(long long ld, long long n_loc, int dtype);
+int tal_update_colsum_lower_dense(int rule, void* cov, long long ld, long long row0, long long n_loc, long long N,
+                                  const void* kvec, const void* wvec, const unsigned char* roi_mask,
+                                  const double* w_pt, const double* dinv, double p0, double p1, double* part,
+                                  int n_split, double* rowpart, double* c_out, int dtype, void* stream);
 int tal_roi_trace(const double* var, const long long* roi_idx, long long m, double* out,
                   void* stream);
 int tal_roi_weights(const double* var, const long long* roi_idx, long long m, int reciprocal,
@@ -561,6 +572,10 @@ typedef struct tal_step_ctx {
   long long scal_ok;                 /* scal holds mean[:, combined.idx] */
   const unsigned char *sel_safe, *sel_sample; long long sel_fc;  /* masks the selection was made under */
   void* fz_scratch;                  /* tal_fused_scratch_bytes(q, ncols, n_split) */
+  /* fused_observe and fused_partial do not depend on each other (the scoring pass needs the column of the
+   * conditioning factor, not the observed row): the scoring pass runs on a side stream between two events.
+   * Library-owned handles, created on first use (zero-initialise); overlap == 0 keeps one stream. */
+  void *side_stream, *ev_fork, *ev_join; long long overlap;
 } tal_step_ctx;
 /* diagnostic (TAL_BREAKDOWN=1): mean microseconds per phase of the recorded fused steps -- [0] peer push + record
  * combine, [1] fused_observe (+ row wait), [2] fused_partial, [3] fused_finish (+ arg-max, publish), [4] covariance

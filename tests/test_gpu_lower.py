@@ -187,3 +187,49 @@ def test_dense_roi_row_reduce_lower_matches_full(cuda, dtype, frac):
         Fl2 = low.score_rows(rule, roi, m, **kw)
         torch.testing.assert_close(Fl, Ff, **tol)
         assert torch.equal(Fl, Fl2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("arith", ["fma", "two_rounding"])
+def test_fused_update_and_dense_row_reduce(cuda, dtype, arith, monkeypatch):
+    """A VTL-type step in lower storage with a large ROI: the ONE pending rank-1 update and both halves of the next
+    score in one pass over the matrix (tal_update_colsum_lower_dense).  Same scores as update-then-score (the sums
+    run over the same updated values; only the summation order of the partials differs), and the matrix is
+    bit-identical to the one the separate update pass produces."""
+    from talgp import _abi
+    from talgp.engine import DeviceGP
+    N, q = 2100, 2
+    rng = np.random.default_rng(9)
+    dom = torch.as_tensor(rng.random((N, 3)), device=cuda)
+
+    def make():
+        gp = DeviceGP(N, q, dtype=dtype, device=cuda, storage="lower", arith=arith)
+        for i in range(q):
+            gp.build_gram(i, _abi.KERNEL_MATERN52 if i == 0 else _abi.KERNEL_GAUSSIAN, 1.0 + 0.5 * i, 0.3 + 0.1 * i, dom)
+        gp.rho.fill_(0.1)
+        gp.init_bounds([2.0] * q)
+        return gp
+
+    fused, plain = make(), make()
+    m = 1700
+    roi = torch.as_tensor(np.sort(rng.choice(N, m, replace=False)), device=cuda)
+    tol = dict(rtol=1e-11, atol=1e-12) if dtype == torch.float64 else dict(rtol=2e-5, atol=1e-6)
+    rules = ((_abi.RULE_VTL, {}), (_abi.RULE_CTL, {}), (_abi.RULE_MMITL, {}), (_abi.RULE_TRUVAR, dict(p0=[1.5, 1.5], p1=0.01)))
+    for step, (rule, kw) in enumerate(rules * 2):
+        idx = int(rng.integers(N))
+        y = rng.standard_normal(q)
+        for g in (fused, plain):
+            g.observe(idx, y, [2.0] * q)
+        assert fused._pending == 1 and plain._pending == 1
+        monkeypatch.setenv("TAL_FUSED_VTL", "1")
+        Ff = fused.score_rows(rule, roi, m, **kw)
+        assert fused._pending == 0
+        monkeypatch.setenv("TAL_FUSED_VTL", "0")
+        Fp = plain.score_rows(rule, roi, m, **kw)
+        torch.testing.assert_close(Ff, Fp, **tol)
+        blk = int(fused.lib.tal_sym_block(fused.dt))
+        r = torch.arange(N, device=cuda)
+        kept = torch.arange(fused.ld, device=cuda)[None, :] < torch.clamp((r // blk + 1) * blk, max=fused.ld)[:, None]
+        assert torch.equal(fused._cov[:, kept], plain._cov[:, kept]), step
+    for name in ("mean", "var", "l", "u"):
+        assert torch.equal(getattr(fused, name), getattr(plain, name)), name

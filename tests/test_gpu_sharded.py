@@ -191,10 +191,51 @@ def test_drop_in_api_row_sharded(cuda, name, storage):
         row0, n_loc = m.row_range
         if storage == "full":
             torch.testing.assert_close(m.covariances, m1.covariances[:, row0:row0 + n_loc], rtol=1e-10, atol=1e-13)
-        else:  # the kept blocks (the sharded model cannot mirror: the images live on other ranks)
-            with pytest.raises(NotImplementedError):
-                m.covariances
+        else:  # the kept blocks (`m.covariances` is a collective here: see the test below)
             full = m1.covariances[:, row0:row0 + n_loc]
             mine = m._gp.cov[:, :, : m.n]
             low = torch.tril(torch.ones((m.n, m.n), dtype=torch.bool, device=cuda))[row0:row0 + n_loc]
             torch.testing.assert_close(mine[:, low], full[:, low], rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("storage", ["lower", "full"])
+def test_sharded_model_serves_full_rows_and_sqd_correlation(cuda, storage):
+    """`model.covariances` (this rank's rows, complete) and `sqd_correlation` on a row-sharded model: in
+    lower-block storage the mirror images of a rank's rows live on the later ranks and are assembled by the
+    symmetric row gather + a sum over the shards (collective); same values as the single-GPU model."""
+    import problems
+    from talgp.dist import ThreadComm
+    G = 3
+    p = problems.c4(T=4)
+    model1, alg1, f1 = problems.build_cuda(p, storage=storage)
+    for t in range(4):
+        alg1.step(f1)
+    cov1 = model1.covariances.clone()
+    X = model1.domain[[3, 50, 177, 399]]
+    A = model1.domain[[0, 9, 120]]
+    sq1 = model1.sqd_correlation(X, A)
+    shared = {"slots": [None] * G, "barrier": threading.Barrier(G)}
+    out, errs = [None] * G, []
+
+    def worker(rank):
+        try:
+            torch.cuda.set_device(cuda)
+            comm = ThreadComm(shared, rank, G)
+            model, alg, f = problems.build_cuda(p, comm=comm, storage=storage)
+            for t in range(4):
+                alg.step(f)
+            cov = model.covariances.clone()   # collective in lower storage
+            sq = model.sqd_correlation(X, A)  # collective
+            out[rank] = (model._gp.row0, model._gp.n_loc, cov, sq)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            shared["barrier"].abort()
+
+    ths = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+    for row0, n_loc, cov, sq in out:
+        torch.testing.assert_close(cov, cov1[:, row0: row0 + n_loc], rtol=1e-12, atol=1e-14)
+        torch.testing.assert_close(sq, sq1, rtol=1e-10, atol=1e-14)

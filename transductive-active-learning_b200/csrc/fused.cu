@@ -141,10 +141,16 @@ __global__ void __launch_bounds__(256)
 fused_partial_kernel(const double* __restrict__ Wb, i64 wb_stride_q, i64 ldw, i64 rows, i64 m_pad,
                      const i64* __restrict__ idx_dev, i64 idx_host, i64 cand0, i64 n_cand,
                      const double* __restrict__ pcol, i64 pcol_stride, i64 ncols, double* __restrict__ part,
-                     double* __restrict__ colsq, int n_split, i64 per) {
+                     double* __restrict__ colsq, int n_split, i64 per, void* wait_box, int G) {
   extern __shared__ double csm[];
   __shared__ double sh[33];
   const int gp = blockIdx.z;
+  if (wait_box) {  // running beside fused_observe: wait for the pieces of this row exchange here as well
+    PeerHeader* h = hdr(wait_box);
+    if ((int)threadIdx.x < G && !spin_until(&h->row_seq[threadIdx.x], h->row_step + 1))
+      h->error = TAL_PEER_ERR_ROW_TIMEOUT;
+    __syncthreads();
+  }
   const i64 j0 = (i64)blockIdx.y * per;
   const i64 j1 = j0 + per < rows ? j0 + per : rows;
   const double* Wg = Wb + (i64)gp * wb_stride_q;
@@ -345,7 +351,7 @@ int fused_observe_y(const void* wbuf, i64 ld, i64 N, int q, const i64* idx_dev, 
 
 int fused_partial(const double* Wb, i64 wb_stride_q, i64 ldw, i64 rows, i64 m_pad, const i64* idx_dev, i64 idx_host,
                   i64 cand0, i64 n_cand, const double* pcol, i64 pcol_stride, i64 ncols, double* part,
-                  double* colsq, int n_split, int q, cudaStream_t st) {
+                  double* colsq, int n_split, int q, cudaStream_t st, void* wait_box, int G) {
   const i64 per = ((rows + n_split - 1) / n_split + 7) / 8 * 8;
   const size_t smem = (size_t)per * sizeof(double);
   if (smem > 200 * 1024) {
@@ -359,7 +365,7 @@ int fused_partial(const double* Wb, i64 wb_stride_q, i64 ldw, i64 rows, i64 m_pa
   }
   dim3 grid((unsigned)((ncols / 2 + 255) / 256), (unsigned)n_split, q);
   fused_partial_kernel<<<grid, 256, smem, st>>>(Wb, wb_stride_q, ldw, rows, m_pad, idx_dev, idx_host, cand0, n_cand,
-                                                pcol, pcol_stride, ncols, part, colsq, n_split, per);
+                                                pcol, pcol_stride, ncols, part, colsq, n_split, per, wait_box, G);
   TAL_LAUNCH_CHECK("fused_partial");
   return TAL_OK;
 }

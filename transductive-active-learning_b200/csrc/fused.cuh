@@ -39,9 +39,11 @@ int fused_observe(const FusedObs& a, int q, int dtype, cudaStream_t st);
 int fused_observe_y(const void* wbuf, i64 ld, i64 N, int q, const i64* idx_dev, i64 idx_host, const double* y,
                     i64 y_stride, int y_gather, const BetaQ& beta, const double* scal, const double* var,
                     double* mean, double* l, double* u, int dtype, cudaStream_t st);
+// wait_box != null: the kernel itself waits for the G pieces of the current row exchange (the peer-supplied column
+// pcol travels with them) -- needed when it does not run behind fused_observe in stream order
 int fused_partial(const double* Wb, i64 wb_stride_q, i64 ldw, i64 rows, i64 m_pad, const i64* idx_dev, i64 idx_host,
                   i64 cand0, i64 n_cand, const double* pcol, i64 pcol_stride, i64 ncols, double* part,
-                  double* colsq, int n_split, int q, cudaStream_t st);
+                  double* colsq, int n_split, int q, cudaStream_t st, void* wait_box = nullptr, int G = 1);
 int fused_finish(const FusedFin& a, int dtype, cudaStream_t st);
 int fused_stash_mean(const double* mean, i64 N, int q, const i64* idx_dev, i64 idx_host, double* scal, cudaStream_t st);
 

@@ -143,8 +143,13 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
   // any data for this peer in this block?  (uniform per block except at piece boundaries)
   const int any = __syncthreads_or((mine || col_mine) ? 1 : 0);
   if (any) {
-    if (threadIdx.x == 0 && !spin_until(&me->ready[g], s)) me->error = TAL_PEER_ERR_READY_TIMEOUT;
-    __syncthreads();
+    // "peer g's row buffer is free": with COMBINE this block has already seen peer g's arg-max record of this
+    // step, which the last block of g's fused_finish publishes AFTER every block of it has read kbuf / wbuf /
+    // pcol of the previous exchange -- the record implies the buffer is free, no second wait over NVLink
+    if constexpr (!COMBINE) {
+      if (threadIdx.x == 0 && !spin_until(&me->ready[g], s)) me->error = TAL_PEER_ERR_READY_TIMEOUT;
+      __syncthreads();
+    }
     char* box = reinterpret_cast<char*>(boxes[g]);
     if (mine) *reinterpret_cast<V16*>(reinterpret_cast<T*>(box + kbuf_off) + (i64)gp * ld + base) = v;
     if (col_mine)

@@ -256,6 +256,132 @@ colsum_cols_dense_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, i64 N,
   if (lane == 0) out[r] = accumulate ? out[r] + acc : acc;
 }
 
+// ONE pass for a VTL-type step in lower-block storage with an ROI that covers a large part of the domain: the
+// single pending rank-1 update (k, w of the last observation) is applied to every kept entry of one GP and BOTH
+// halves of the next score are accumulated from the updated values on the way --
+//   kept part of the ROI rows:   part[s][x]    = sum_{a in split s, a in ROI} elem(v'[a][x], w_a, dinv[x])
+//   mirrored part of row r:      rowpart[t][r] = sum_{c in tile t, c in ROI, c < blockstart(r)} elem(v'[r][c], w_c, dinv[r])
+// -- instead of an update pass (read + write) followed by two read passes (tal_rankb_update +
+// tal_colsum_lower_dense): 2 instead of 4 transfers of the matrix per step.  The update is the same rounded
+// operation as in rank1.cu / rankb.cu (sub_prod_m<FMA> in T): the matrix stays bit-identical.
+// grid (column tiles of 256 vectors, row splits of `per` rows); dynamic shared memory: per * (2 + 8) doubles + per T.
+template <typename T, int RULE, bool HAS_W, bool FMA>
+__global__ void __launch_bounds__(256)
+update_colsum_dense_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N, const T* __restrict__ kvec,
+                           const T* __restrict__ wvec, const unsigned char* __restrict__ roi_mask,
+                           const double* __restrict__ w_pt, const double* __restrict__ dinv, double p0, double p1,
+                           double* __restrict__ part, double* __restrict__ rowpart, i64 per) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
+  constexpr int UNROLL = 4;
+  extern __shared__ __align__(16) unsigned char ucd_smem[];
+  double* wrow = reinterpret_cast<double*>(ucd_smem);  // [per] weight of row a as a TARGET (0 with mask_row = 0)
+  double* drow = wrow + per;                            // [per] dinv of row r as a CANDIDATE
+  double* racc = drow + per;                            // [per][8] mirrored sums per warp
+  T* krow = reinterpret_cast<T*>(racc + per * 8);       // [per]
+  unsigned char* mrow = reinterpret_cast<unsigned char*>(krow + per);  // [per]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  i64 j0 = (i64)blockIdx.y * per, j1 = j0 + per;
+  if (j1 > n_loc) j1 = n_loc;
+  const i64 tile0 = (i64)blockIdx.x * 256 * VN;
+  // the whole tile lies above the diagonal blocks of every row of this split: nothing kept, nothing to add
+  const bool tile_dead = tile0 >= (((row0 + j1 - 1) >> 5) + 1) << 5;
+  for (i64 j = j0 + threadIdx.x; j < j1; j += 256) {
+    const i64 a = row0 + j;
+    mrow[j - j0] = roi_mask[a];
+    wrow[j - j0] = HAS_W ? w_pt[a] : 1.0;
+    drow[j - j0] = dinv ? dinv[a] : 0.0;
+    krow[j - j0] = kvec[a];
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) racc[(j - j0) * 8 + w8] = 0.0;
+  }
+  __syncthreads();
+  const i64 col = tile0 + (i64)threadIdx.x * VN;
+  double acc[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) acc[e] = 0.0;
+  if (!tile_dead) {
+    T wc[VN];
+    double dic[VN], wpc[VN];
+    bool mc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      const bool in = col + e < N;
+      wc[e] = col + e < ld ? wvec[col + e] : T(0);
+      dic[e] = (dinv && in) ? dinv[col + e] : 0.0;
+      mc[e] = in && roi_mask[col + e] != 0;
+      wpc[e] = (HAS_W && in) ? w_pt[col + e] : 1.0;
+    }
+    // warp-uniform row range: the first row that keeps the warp's first column
+    const i64 wcol0 = tile0 + (i64)warp * 32 * VN;
+    i64 js = ((wcol0 >> 5) << 5) - row0;
+    if (js < j0) js = j0;
+    for (i64 j = js; j < j1; j += UNROLL) {
+      V c[UNROLL];
+      bool ok[UNROLL];
+#pragma unroll
+      for (int t = 0; t < UNROLL; ++t) {
+        const i64 a = row0 + j + t;
+        ok[t] = j + t < j1 && col < ld && col < ((a >> 5) + 1) << 5;
+        if (ok[t]) c[t] = ld_stream(reinterpret_cast<const V*>(cov + (j + t) * ld + col));
+      }
+#pragma unroll
+      for (int t = 0; t < UNROLL; ++t) {
+        if (j + t >= j1) break;  // (warp-uniform)
+        const i64 jl = j + t - j0;
+        const i64 a = row0 + j + t;
+        double rs = 0.0;
+        if (ok[t]) {
+          T e[VN];
+          memcpy(e, &c[t], sizeof(V));
+          const T kr = krow[jl];
+          const bool ma = mrow[jl] != 0;
+          const double wa = wrow[jl], da = drow[jl];
+          const i64 bstart = (a >> 5) << 5;  // columns before it are the mirrored pairs of row a
+#pragma unroll
+          for (int k = 0; k < VN; ++k) {
+            e[k] = sub_prod_m<FMA>(e[k], kr, wc[k]);
+            const double v = (double)e[k];
+            if (ma) acc[k] += elem<RULE>(v, wa, dic[k], p0, p1);
+            if (mc[k] && col + k < bstart) rs += elem<RULE>(v, wpc[k], da, p0, p1);
+          }
+          V o;
+          memcpy(&o, e, sizeof(V));
+          st_stream(reinterpret_cast<V*>(cov + (j + t) * ld + col), o);
+        }
+        rs = warp_sum(rs);
+        if (lane == 0) racc[jl * 8 + warp] = rs;
+      }
+    }
+  }
+  double* o = part + (i64)blockIdx.y * N;
+#pragma unroll
+  for (int e = 0; e < VN; ++e)
+    if (col + e < N) o[col + e] = acc[e];
+  __syncthreads();
+  for (i64 j = j0 + threadIdx.x; j < j1; j += 256) {
+    const double* r8 = racc + (j - j0) * 8;
+    double sum = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) sum += r8[w8];  // fixed order
+    rowpart[(i64)blockIdx.x * n_loc + j] = sum;
+  }
+}
+
+// c[x] = sum_s part[s][x] + (x in [row0, row0 + n_loc): sum_t rowpart[t][x - row0]), fixed order
+__global__ void __launch_bounds__(256)
+sum_parts2_kernel(const double* __restrict__ part, int n_split, const double* __restrict__ rowpart, int n_tiles,
+                  i64 row0, i64 n_loc, i64 N, double* __restrict__ out) {
+  const i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= N) return;
+  double acc = 0.0;
+  for (int s = 0; s < n_split; ++s) acc += part[(i64)s * N + x];
+  const i64 r = x - row0;
+  if (r >= 0 && r < n_loc)
+    for (int t = 0; t < n_tiles; ++t) acc += rowpart[(i64)t * n_loc + r];
+  out[x] = acc;
+}
+
 // tr_A = sum_{a in roi} var[a]  (one block, deterministic)
 __global__ void __launch_bounds__(256)
 roi_trace_kernel(const double* __restrict__ var, const i64* __restrict__ roi_idx, i64 m,
@@ -527,6 +653,69 @@ int tal_colsum_lower_dense(int rule, const void* cov, long long ld, long long ro
   }
 #undef TAL_CD
   TAL_LAUNCH_CHECK("tal_colsum_lower_dense");
+  return TAL_OK;
+}
+
+long long tal_update_colsum_scratch_bytes(long long ld, long long n_loc, int dtype) {
+  const long long vn = base_dtype(dtype) == TAL_F64 ? 2 : 4;
+  const long long tiles = (ld + 256 * vn - 1) / (256 * vn);
+  return tiles * (n_loc > 0 ? n_loc : 1) * (long long)sizeof(double);
+}
+
+int tal_update_colsum_lower_dense(int rule, void* cov, long long ld, long long row0, long long n_loc, long long N,
+                                  const void* kvec, const void* wvec, const unsigned char* roi_mask,
+                                  const double* w_pt, const double* dinv, double p0, double p1, double* part,
+                                  int n_split, double* rowpart, double* c_out, int dtype, void* stream) {
+  TAL_ARG(cov && kvec && wvec && roi_mask && part && rowpart && c_out);
+  TAL_ARG(n_split >= 1 && n_split <= 65535 && ld % 32 == 0 && ld >= N && n_loc >= 0 && row0 % 32 == 0);
+  TAL_ARG(rule >= TAL_RULE_VTL && rule <= TAL_RULE_TRUVAR);
+  const bool fma_mode = arith_fma(dtype);
+  dtype = base_dtype(dtype);
+  TAL_ARG(dtype == TAL_F64 || dtype == TAL_F32);
+  TAL_ARG(tal_sym_block(dtype) == 32);
+  cudaStream_t st = as_stream(stream);
+  const i64 vn = dtype == TAL_F64 ? 2 : 4;
+  const i64 s_el = dtype == TAL_F64 ? 8 : 4;
+  const i64 per = (n_loc + n_split - 1) / n_split > 0 ? (n_loc + n_split - 1) / n_split : 1;
+  const int tiles = (int)((ld + 256 * vn - 1) / (256 * vn));
+  const size_t smem = (size_t)per * (10 * sizeof(double) + s_el + 1) + 16;
+  TAL_ARG(smem <= 96 * 1024);
+  dim3 grid((unsigned)tiles, (unsigned)n_split);
+#define TAL_UC3(T, R, W, F)                                                                                   \
+  do {                                                                                                       \
+    auto kern = update_colsum_dense_kernel<T, R, W, F>;                                                      \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      TAL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));          \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    kern<<<grid, 256, smem, st>>>((T*)cov, ld, row0, n_loc, N, (const T*)kvec, (const T*)wvec, roi_mask, w_pt, dinv, \
+                                  p0, p1, part, rowpart, per);                                               \
+  } while (0)
+#define TAL_UC2(T, R, W) do { if (fma_mode) TAL_UC3(T, R, W, true); else TAL_UC3(T, R, W, false); } while (0)
+#define TAL_UC(T, R) do { if (w_pt) TAL_UC2(T, R, true); else TAL_UC2(T, R, false); } while (0)
+  if (n_loc > 0) {
+    if (dtype == TAL_F64) {
+      switch (rule) {
+        case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_UC(double, TAL_RULE_VTL); break;
+        case TAL_RULE_MMITL: TAL_UC(double, TAL_RULE_MMITL); break;
+        default: TAL_UC(double, TAL_RULE_TRUVAR); break;
+      }
+    } else {
+      switch (rule) {
+        case TAL_RULE_VTL: case TAL_RULE_CTL: TAL_UC(float, TAL_RULE_VTL); break;
+        case TAL_RULE_MMITL: TAL_UC(float, TAL_RULE_MMITL); break;
+        default: TAL_UC(float, TAL_RULE_TRUVAR); break;
+      }
+    }
+    TAL_LAUNCH_CHECK("tal_update_colsum_lower_dense");
+  }
+#undef TAL_UC
+#undef TAL_UC2
+#undef TAL_UC3
+  sum_parts2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(part, n_loc > 0 ? n_split : 0, rowpart, tiles, row0,
+                                                                 n_loc, N, c_out);
+  TAL_LAUNCH_CHECK("tal_update_colsum_lower_dense/sum");
   return TAL_OK;
 }
 

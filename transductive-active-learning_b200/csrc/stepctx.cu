@@ -183,19 +183,50 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
   o.y = y_dev; o.y_stride = y_stride; o.y_gather = y_gather;
   for (int i = 0; i < TAL_MAX_Q; ++i) o.beta.v[i] = c->beta[i];
   o.mailbox = c->G > 1 ? c->mailbox : nullptr; o.G = (int)c->G; o.wait = cond ? 1 : 0;
+  // fused_observe (needs the row) and fused_partial (needs the factor's column) are independent: with `overlap` the
+  // scoring pass is forked onto a side stream before fused_observe and joined before fused_finish
+  bool forked = false;
+  if (cond && c->overlap != 0) {
+    if (!c->side_stream) {
+      cudaStream_t s2; cudaEvent_t e1, e2;
+      TAL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      TAL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      TAL_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      c->side_stream = s2; c->ev_fork = e1; c->ev_join = e2;
+    }
+    forked = true;
+  }
+  double* part = nullptr;
+  double* colsq = nullptr;
+  if (cond) {
+    double* base = (double*)((char*)c->fz_scratch + sizeof(FusedScratch));
+    colsq = base + 8;
+    part = colsq + (((long long)q * c->n_split + 1) & ~1LL);  // (16-byte aligned: double2 stores)
+  }
+  if (forked) {
+    cudaStream_t s2 = (cudaStream_t)c->side_stream;
+    TAL_CUDA(cudaEventRecord((cudaEvent_t)c->ev_fork, st));
+    TAL_CUDA(cudaStreamWaitEvent(s2, (cudaEvent_t)c->ev_fork, 0));
+    rc = fused_partial(c->Wb, c->cap_rows * c->ldw, c->ldw, c->rows, c->m_pad, idx_dev, idx_host, c->cand0, c->n_cand,
+                       c->G > 1 ? c->pcol_peer : nullptr, c->pcol_stride, c->ncols, part, colsq, (int)c->n_split, q,
+                       s2, c->G > 1 ? c->mailbox : nullptr, (int)c->G);
+    if (rc != TAL_OK) return rc;
+    TAL_CUDA(cudaEventRecord((cudaEvent_t)c->ev_join, s2));
+  }
   rc = fused_observe(o, q, upd_dtype(c), st);
   if (rc != TAL_OK) return rc;
   bd_mark(2, st);
   c->scal_ok = 0;
   c->sel_state = 0;
   if (cond) {
-    double* base = (double*)((char*)c->fz_scratch + sizeof(FusedScratch));
-    double* colsq = base + 8;
-    double* part = colsq + (((long long)q * c->n_split + 1) & ~1LL);  // (16-byte aligned: double2 stores)
-    rc = fused_partial(c->Wb, c->cap_rows * c->ldw, c->ldw, c->rows, c->m_pad, idx_dev, idx_host, c->cand0, c->n_cand,
-                       c->G > 1 ? c->pcol_peer : nullptr, c->pcol_stride, c->ncols, part, colsq, (int)c->n_split, q,
-                       st);
-    if (rc != TAL_OK) return rc;
+    if (forked) {
+      TAL_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)c->ev_join, 0));
+    } else {
+      rc = fused_partial(c->Wb, c->cap_rows * c->ldw, c->ldw, c->rows, c->m_pad, idx_dev, idx_host, c->cand0, c->n_cand,
+                         c->G > 1 ? c->pcol_peer : nullptr, c->pcol_stride, c->ncols, part, colsq, (int)c->n_split, q,
+                         st);
+      if (rc != TAL_OK) return rc;
+    }
     bd_mark(3, st);
     const bool select = c->auto_select != 0 && y_dev != nullptr;  // (l, u are final only once y has been applied)
     FusedFin f;

@@ -195,11 +195,14 @@ class MarginalModel(Model):
         MM-ITL rules use the streaming row-reduce kernels instead)."""
         if A is None:
             A = X
-        if self._gp.sharded:
-            raise NotImplementedError("sqd_correlation needs full covariance rows (row-sharded model)")
         X_idx = self.get_indices(X)
         A_idx = self.get_indices(A)
-        cov = self.covariances[:, X_idx][:, :, A_idx].to(torch.float64)  # [q, n, m]
+        if self._gp.sharded:  # the rows of X are assembled from the shards (collective), 256 at a time
+            gp = self._gp
+            cov = torch.stack([torch.cat([gp.gather_full_rows(i, X_idx[s: s + 256])[:, A_idx].clone()
+                                          for s in range(0, X_idx.numel(), 256)]) for i in range(self.q)])
+        else:
+            cov = self.covariances[:, X_idx][:, :, A_idx].to(torch.float64)  # [q, n, m]
         sqd = torch.square(cov)
         noise = self.noise_rate.at(X.points if isinstance(X, ROI) else as_f64(X))
         var_X = self.variances[:, X_idx]

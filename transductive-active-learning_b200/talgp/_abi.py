@@ -60,6 +60,7 @@ class StepCtx(C.Structure):
         + [("ev_updates", C.c_longlong * 64)]
         + [(n, C.c_longlong) for n in ("arith", "auto_select", "sel_state", "scal_ok")]
         + [("sel_safe", C.c_void_p), ("sel_sample", C.c_void_p), ("sel_fc", C.c_longlong), ("fz_scratch", C.c_void_p)]
+        + [("side_stream", C.c_void_p), ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p), ("overlap", C.c_longlong)]
     )
 
 
@@ -100,6 +101,9 @@ SIGNATURES = {
                               _i, _p]),
     "tal_colsum_lower_dense": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _ll, _p, _p, _p, _p, _d, _d, _p, _i, _p,
                                     _i, _p]),
+    "tal_update_colsum_scratch_bytes": (_ll, [_ll, _ll, _i]),
+    "tal_update_colsum_lower_dense": (_i, [_i, _p, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _d, _d, _p, _i, _p, _p,
+                                           _i, _p]),
     "tal_colsum_cols": (_i, [_i, _p, _ll, _ll, _p, _ll, _p, _p, _d, _d, _p, _i, _p]),
     "tal_roi_trace": (_i, [_p, _p, _ll, _p, _p]),
     "tal_roi_weights": (_i, [_p, _p, _ll, _i, _p, _p]),

@@ -125,31 +125,31 @@ class ThreadComm:
     def sum_(self, buf: torch.Tensor) -> torch.Tensor:
         sh = self.shared
         sh["slots"][self.rank] = buf
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         tot = sh["slots"][0].clone()
         for r in range(1, self.world):
             tot += sh["slots"][r]
-        sh["barrier"].wait()  # every thread has issued its reads
+        sh["barrier"].wait(120)  # every thread has issued its reads
         buf.copy_(tot)
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         return buf
 
     def gather_records(self, rec: torch.Tensor, out: torch.Tensor) -> None:
         sh = self.shared
         sh["slots"][self.rank] = rec
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         for r in range(self.world):
             out[r].copy_(sh["slots"][r])
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
 
     def all_gather_(self, part: torch.Tensor, out: torch.Tensor) -> None:
         sh = self.shared
         sh["slots"][self.rank] = part
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         n = part.numel()
         for r in range(self.world):
             out[r * n:(r + 1) * n].copy_(sh["slots"][r])
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
 
 
 # ------------------------------------------------------ NVLink peer-memory exchange
@@ -294,14 +294,14 @@ class LocalPeerComm(_PeerMixin, ThreadComm):
         self._peer_init()
 
     def _host_barrier(self):
-        self.shared["barrier"].wait()
+        self.shared["barrier"].wait(120)
 
     def _exchange_ptrs(self, own_ptr: int):
         sh = self.shared
         sh["slots"][self.rank] = own_ptr
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         ptrs = [int(sh["slots"][r]) for r in range(self.world)]
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         return ptrs
 
     # ThreadComm's collectives rely on one shared stream (issue order = execution
@@ -310,37 +310,37 @@ class LocalPeerComm(_PeerMixin, ThreadComm):
         sh, st = self.shared, torch.cuda.current_stream()
         st.synchronize()
         sh["slots"][self.rank] = buf
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         tot = sh["slots"][0].clone()
         for r in range(1, self.world):
             tot += sh["slots"][r]
         st.synchronize()
-        sh["barrier"].wait()  # every thread has finished reading
+        sh["barrier"].wait(120)  # every thread has finished reading
         buf.copy_(tot)
         st.synchronize()
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         return buf
 
     def all_gather_(self, part, out):
         sh, st = self.shared, torch.cuda.current_stream()
         st.synchronize()
         sh["slots"][self.rank] = part
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         n = part.numel()
         for r in range(self.world):
             out[r * n:(r + 1) * n].copy_(sh["slots"][r])
         st.synchronize()
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
 
     def gather_records(self, rec, out):
         sh, st = self.shared, torch.cuda.current_stream()
         st.synchronize()
         sh["slots"][self.rank] = rec
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
         for r in range(self.world):
             out[r].copy_(sh["slots"][r])
         st.synchronize()
-        sh["barrier"].wait()
+        sh["barrier"].wait(120)
 
 
 # ------------------------------------------------------------------ device side

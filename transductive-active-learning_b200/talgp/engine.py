@@ -250,7 +250,11 @@ class DeviceGP:
         if c is None or self._ctx_key != key:
             if c is not None:
                 self._sel_discard()  # (a published selection belongs to the old context)
+            old = c
             c = _abi.StepCtx()
+            if old is not None:  # (library-owned side stream / events of the overlap: keep them)
+                c.side_stream, c.ev_fork, c.ev_join = old.side_stream, old.ev_fork, old.ev_join
+            c.overlap = int(os.environ.get("TAL_OVERLAP", "1") != "0")
             c.cov, c.cov_stride_q, c.ld, c.row0, c.n_loc = self._cov.data_ptr(), self.cov_stride_q, self.ld, self.row0, self.n_loc
             c.N, c.q, c.dtype, c.lower = self.N, self.q, self.dt, int(self.lower)
             c.arith = int(self.arith == "fma")
@@ -446,11 +450,37 @@ class DeviceGP:
         if not (self.lower and self._upper_stale):
             return
         if self.comm is not None:
-            raise NotImplementedError("this operation reads full covariance rows; a row-sharded model in "
-                                      "lower-block storage holds the mirror images on other ranks")
+            # row-sharded: the mirror images of this rank's rows live in the later rows of OTHER ranks.  Every
+            # global row is assembled 256 at a time by the symmetric row gather + a sum over the shards, its owner
+            # keeps it.  COLLECTIVE (every rank must call it) and O(N^2) traffic through the all-reduce: a one-off
+            # reader (`model.covariances`), not a per-step path.
+            for i in range(self.q):
+                for a in range(0, self.N, 256):
+                    idx = torch.arange(a, min(self.N, a + 256), device=self.device)
+                    rows = self.gather_full_rows(i, idx)
+                    lo, hi = max(a, self.row0), min(a + idx.numel(), self.row0 + self.n_loc)
+                    if lo < hi:
+                        self._cov[i, lo - self.row0: hi - self.row0, : self.N].copy_(
+                            rows[lo - a: hi - a, : self.N].to(self.dtype))  # (pad columns stay zero)
+            self._upper_stale = False
+            return
         _abi.check(self.lib.tal_sym_mirror(_ptr(self._cov), self.cov_stride_q, self.ld, self.N, self.q,
                                            self.dt, _stream()), "tal_sym_mirror")
         self._upper_stale = False
+
+    def gather_full_rows(self, i: int, idx: torch.Tensor) -> torch.Tensor:
+        """Full rows cov_i[idx, :] ([len(idx), ld] fp64) on every rank, whatever the storage mode and the sharding:
+        every shard contributes the pieces it holds (tal_gather_rows[_lower]), a sum over the shards completes
+        them.  Collective when row-sharded.  Up to 256 rows per call."""
+        self.flush()
+        idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+        m = int(idx.numel())
+        rows = self._scratch("full_rows", (max(m, 1), self.ld))
+        gather = self.lib.tal_gather_rows_lower if self.lower else self.lib.tal_gather_rows
+        _abi.check(gather(_ptr(self._cov[i]), self.ld, self.row0, self.n_loc, self.N, _ptr(idx), m, _ptr(rows),
+                          self.ld, self.dt, _stream()), "tal_gather_rows")
+        self._sum(rows)
+        return rows[:m]
 
     def update_bytes(self) -> float:
         """Algorithmic HBM bytes of one posterior update of this shard (read + write
@@ -698,6 +728,10 @@ class DeviceGP:
         F is [n_loc] for candidates row0..row0+n_loc (symmetric column gather)."""
         lib = self.lib
         N = self.N
+        if self.lower and self._pending == 1 and 4 * m >= N and os.environ.get("TAL_FUSED_VTL", "1") != "0":
+            # a VTL-type step: ONE pending update and an ROI that covers most of the domain -- the update pass and
+            # both halves of the score in one transfer of the matrix (tal_update_colsum_lower_dense)
+            return self._score_rows_lower(rule, roi_idx, m, p0, p1, roi_mask, fuse_update=True)
         self.flush()
         if self.lower:
             return self._score_rows_lower(rule, roi_idx, m, p0, p1, roi_mask)
@@ -746,7 +780,7 @@ class DeviceGP:
         return F
 
     def _score_rows_lower(self, rule: int, roi_idx: torch.Tensor, m: int, p0=None, p1: float = 0.0,
-                          roi_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                          roi_mask: Optional[torch.Tensor] = None, fuse_update: bool = False) -> torch.Tensor:
         """The row-reduce rules in lower-block storage: every pair (a, x) of a target point and a
         candidate is kept either in row a (x below the end of a's diagonal block) or in row x;
         `tal_colsum_lower` sums what this shard keeps over all N candidates, a sum over the shards
@@ -789,7 +823,14 @@ class DeviceGP:
                 _abi.check(lib.tal_pred_var_inv(_ptr(self.var[i]), _ptr(self.rho[i]), N,
                                                 _ptr(dinv), _stream()), "tal_pred_var_inv")
             pp0 = float(p0[i]) if p0 is not None else 0.0
-            if dense:
+            if fuse_update:
+                rowpart = self._scratch("score_rowpart", (int(lib.tal_update_colsum_scratch_bytes(
+                    self.ld, self.n_loc, self.dt)) // 8,))
+                _abi.check(lib.tal_update_colsum_lower_dense(
+                    rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(self._Kp[0, i]),
+                    _ptr(self._Wp[0, i]), _ptr(roi_mask), _ptr(w_pt), _ptr(dinv), pp0, float(p1), _ptr(part),
+                    n_split, _ptr(rowpart), _ptr(c), self.dt_upd, _stream()), "tal_update_colsum_lower_dense")
+            elif dense:
                 _abi.check(lib.tal_colsum_lower_dense(
                     rule, _ptr(self._cov[i]), self.ld, self.row0, self.n_loc, N, _ptr(roi_idx), m, _ptr(roi_mask),
                     _ptr(w), _ptr(w_pt), _ptr(dinv), pp0, float(p1), _ptr(part), n_split, _ptr(c), self.dt,
@@ -806,6 +847,9 @@ class DeviceGP:
             _abi.check(lib.tal_score_rows_finish(
                 rule, _ptr(c[off:]), _ptr(self.var[i, off:]), _ptr(self.rho[i, off:]), _ptr(tr), n_out,
                 1 if i > 0 else 0, _ptr(F), _stream()), "tal_score_rows_finish")
+        if fuse_update:  # the pending update went into the matrix with the pass above
+            self._pending = 0
+            self._upper_stale = True
         return F
 
     def _cond_dims(self, m: int):
