@@ -266,16 +266,16 @@ colsum_cols_dense_kernel(const T* __restrict__ cov, i64 ld, i64 n_loc, i64 N,
 // operation as in rank1.cu / rankb.cu (sub_prod_m<FMA> in T): the matrix stays bit-identical.
 // grid (column tiles of 256 vectors, row splits of `per` rows); dynamic shared memory: per * (2 + 8) doubles + per T.
 template <typename T, int RULE, bool HAS_W, bool FMA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 update_colsum_dense_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64 N, const T* __restrict__ kvec,
                            const T* __restrict__ wvec, const unsigned char* __restrict__ roi_mask,
                            const double* __restrict__ w_pt, const double* __restrict__ dinv, double p0, double p1,
                            double* __restrict__ part, double* __restrict__ rowpart, i64 per) {
   typedef typename Vec16<T>::type V;
   constexpr int VN = Vec16<T>::n;
-  constexpr int UNROLL = 4;
+  constexpr int UNROLL = 8;  // rows in flight per thread; their 8 row sums share ONE butterfly reduction
   extern __shared__ __align__(16) unsigned char ucd_smem[];
-  double* wrow = reinterpret_cast<double*>(ucd_smem);  // [per] weight of row a as a TARGET (0 with mask_row = 0)
+  double* wrow = reinterpret_cast<double*>(ucd_smem);  // [per] weight of row a as a TARGET
   double* drow = wrow + per;                            // [per] dinv of row r as a CANDIDATE
   double* racc = drow + per;                            // [per][8] mirrored sums per warp
   T* krow = reinterpret_cast<T*>(racc + per * 8);       // [per]
@@ -325,13 +325,13 @@ update_colsum_dense_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64
         ok[t] = j + t < j1 && col < ld && col < ((a >> 5) + 1) << 5;
         if (ok[t]) c[t] = ld_stream(reinterpret_cast<const V*>(cov + (j + t) * ld + col));
       }
+      double rs[UNROLL];
 #pragma unroll
       for (int t = 0; t < UNROLL; ++t) {
-        if (j + t >= j1) break;  // (warp-uniform)
-        const i64 jl = j + t - j0;
-        const i64 a = row0 + j + t;
-        double rs = 0.0;
+        rs[t] = 0.0;
         if (ok[t]) {
+          const i64 jl = j + t - j0;
+          const i64 a = row0 + j + t;
           T e[VN];
           memcpy(e, &c[t], sizeof(V));
           const T kr = krow[jl];
@@ -343,15 +343,37 @@ update_colsum_dense_kernel(T* __restrict__ cov, i64 ld, i64 row0, i64 n_loc, i64
             e[k] = sub_prod_m<FMA>(e[k], kr, wc[k]);
             const double v = (double)e[k];
             if (ma) acc[k] += elem<RULE>(v, wa, dic[k], p0, p1);
-            if (mc[k] && col + k < bstart) rs += elem<RULE>(v, wpc[k], da, p0, p1);
+            if (mc[k] && col + k < bstart) rs[t] += elem<RULE>(v, wpc[k], da, p0, p1);
           }
           V o;
           memcpy(&o, e, sizeof(V));
           st_stream(reinterpret_cast<V*>(cov + (j + t) * ld + col), o);
         }
-        rs = warp_sum(rs);
-        if (lane == 0) racc[jl * 8 + warp] = rs;
       }
+      // 8 row sums over 32 lanes in 9 exchanges: halve the set of rows a lane carries at every step (lane bits
+      // 4, 3, 2 pick the row), then finish over the lanes that differ in bits 1, 0.  Fixed order: deterministic.
+      double k4[4], k2[2], k1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double send = (lane & 16) ? rs[i] : rs[i + 4];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        k4[i] = ((lane & 16) ? rs[i + 4] : rs[i]) + recv;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double send = (lane & 8) ? k4[i] : k4[i + 2];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        k2[i] = ((lane & 8) ? k4[i + 2] : k4[i]) + recv;
+      }
+      {
+        const double send = (lane & 4) ? k2[0] : k2[1];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        k1 = ((lane & 4) ? k2[1] : k2[0]) + recv;
+      }
+      k1 += __shfl_xor_sync(0xffffffffu, k1, 2);
+      k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+      const int trow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      if ((lane & 3) == 0 && j + trow < j1) racc[(j + trow - j0) * 8 + warp] = k1;
     }
   }
   double* o = part + (i64)blockIdx.y * N;

@@ -139,6 +139,13 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
     c->cond_valid = 0;
   }
   if (cond) TAL_ARG(c->fz_scratch && c->cs && (c->auto_select == 0 || (c->F && c->rec && c->combined)));
+  if (cond && c->overlap != 0 && !c->side_stream) {  // (created before anything of this step is enqueued)
+    cudaStream_t s2; cudaEvent_t e1, e2;
+    TAL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    TAL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+    TAL_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    c->side_stream = s2; c->ev_fork = e1; c->ev_join = e2;
+  }
   const bool own = idx_dev != nullptr && c->combined != nullptr && idx_dev == &c->combined->idx;
   int rc;
   if (c->sel_state == 1 && !(own && masks_match(c))) {  // a published selection nobody will use: consume it
@@ -185,17 +192,7 @@ int tal_ctx_observe(tal_step_ctx* c, const long long* idx_dev, long long idx_hos
   o.mailbox = c->G > 1 ? c->mailbox : nullptr; o.G = (int)c->G; o.wait = cond ? 1 : 0;
   // fused_observe (needs the row) and fused_partial (needs the factor's column) are independent: with `overlap` the
   // scoring pass is forked onto a side stream before fused_observe and joined before fused_finish
-  bool forked = false;
-  if (cond && c->overlap != 0) {
-    if (!c->side_stream) {
-      cudaStream_t s2; cudaEvent_t e1, e2;
-      TAL_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-      TAL_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-      TAL_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-      c->side_stream = s2; c->ev_fork = e1; c->ev_join = e2;
-    }
-    forked = true;
-  }
+  const bool forked = cond && c->overlap != 0;
   double* part = nullptr;
   double* colsq = nullptr;
   if (cond) {

@@ -289,6 +289,8 @@ class LocalPeerComm(_PeerMixin, ThreadComm):
     kernels of different shards must run concurrently: they wait on each other).
     Pointers are shared directly; used to test csrc/peer.cu on a single GPU."""
 
+    single_context = True  # every shard lives in ONE CUDA context: see DeviceGP._ctx_get (no side stream)
+
     def __init__(self, shared: dict, rank: int, world: int):
         ThreadComm.__init__(self, shared, rank, world)
         self._peer_init()

@@ -139,6 +139,7 @@ class DeviceGP:
         self._y_dev = torch.zeros((64, q), **f64)  # ring of device slots for host-supplied observations
         self._y_slot, self._y_event = 0, None
         self._ws = {}  # named scratch tensors, grown on demand
+        self._ws_views = {}  # name -> (tensor, shape, dtype, view) of the last request
         self._cond = None  # incremental conditioning state (score_itl_directed)
         self._ctx = None   # tal_step_ctx of the fused step (built on demand)
         self.fused = os.environ.get("TAL_FUSED", "1") != "0"  # False: the kernel-by-kernel Python sequence
@@ -254,7 +255,11 @@ class DeviceGP:
             c = _abi.StepCtx()
             if old is not None:  # (library-owned side stream / events of the overlap: keep them)
                 c.side_stream, c.ev_fork, c.ev_join = old.side_stream, old.ev_fork, old.ev_join
-            c.overlap = int(os.environ.get("TAL_OVERLAP", "1") != "0")
+            # observe / scoring-pass overlap on a side stream -- not in the single-GPU emulation of the peer protocol,
+            # where creating a stream while another shard's kernel spins on this one stalls until its time-out
+            # (the hazard of tests/conftest.py; between processes on separate GPUs nothing is shared)
+            c.overlap = int(os.environ.get("TAL_OVERLAP", "1") != "0"
+                            and not getattr(self.comm, "single_context", False))
             c.cov, c.cov_stride_q, c.ld, c.row0, c.n_loc = self._cov.data_ptr(), self.cov_stride_q, self.ld, self.row0, self.n_loc
             c.N, c.q, c.dtype, c.lower = self.N, self.q, self.dt, int(self.lower)
             c.arith = int(self.arith == "fma")
@@ -423,11 +428,18 @@ class DeviceGP:
     # ------------------------------------------------------------------ util
     def _scratch(self, name: str, shape, dtype=torch.float64) -> torch.Tensor:
         t = self._ws.get(name)
-        n = int(np.prod(shape))
+        hit = self._ws_views.get(name)  # (the same request as last time: the per-step callers)
+        if hit is not None and hit[0] is t and hit[1] == shape and hit[2] is dtype:
+            return hit[3]
+        n = 1
+        for d_ in shape:
+            n *= int(d_)
         if t is None or t.numel() < n or t.dtype != dtype:
             t = torch.empty((n,), dtype=dtype, device=self.device)
             self._ws[name] = t
-        return t[:n].view(*shape)
+        v = t[:n].view(*shape)
+        self._ws_views[name] = (t, tuple(shape), dtype, v)
+        return v
 
     @property
     def cov_stride_q(self) -> int:
