@@ -44,11 +44,11 @@ __global__ void __launch_bounds__(256) fused_observe_kernel(FusedObs a) {
   T* Wslot = a.Wslot ? (T*)a.Wslot + (i64)gp * ld : nullptr;
   if (a.mailbox && a.wait) {  // sharded: the G pieces of the row land in kbuf (inside this rank's mailbox)
     PeerHeader* h = hdr(a.mailbox);
-    if ((int)threadIdx.x < a.G && !spin_until(&h->row_seq[threadIdx.x], h->row_step + 1))
-      h->error = TAL_PEER_ERR_ROW_TIMEOUT;
+    const unsigned long long want = *(const volatile unsigned long long*)&h->row_step + 1;
+    if ((int)threadIdx.x < a.G && !spin_until(&h->row_seq[threadIdx.x], want)) h->error = TAL_PEER_ERR_ROW_TIMEOUT;
     __syncthreads();
   }
-  const i64 idx = a.idx_dev ? *a.idx_dev : a.idx_host;
+  const i64 idx = a.idx_dev ? __ldcg(a.idx_dev) : a.idx_host;
   if (idx < 0 || idx >= N) {  // failed arg-max: the observation is a no-op (k = w = 0 is queued)
     if (b < ld) {
       if (!a.mailbox) kbuf[b] = T(0);
@@ -147,18 +147,20 @@ fused_partial_kernel(const double* __restrict__ Wb, i64 wb_stride_q, i64 ldw, i6
   const int gp = blockIdx.z;
   if (wait_box) {  // running beside fused_observe: wait for the pieces of this row exchange here as well
     PeerHeader* h = hdr(wait_box);
-    if ((int)threadIdx.x < G && !spin_until(&h->row_seq[threadIdx.x], h->row_step + 1))
-      h->error = TAL_PEER_ERR_ROW_TIMEOUT;
+    // (row_step through L2: this kernel runs on a side stream beside other grids; a line of the previous step
+    //  left in an L1 must not decide which exchange is waited for)
+    const unsigned long long want = *(const volatile unsigned long long*)&h->row_step + 1;
+    if ((int)threadIdx.x < G && !spin_until(&h->row_seq[threadIdx.x], want)) h->error = TAL_PEER_ERR_ROW_TIMEOUT;
     __syncthreads();
   }
   const i64 j0 = (i64)blockIdx.y * per;
   const i64 j1 = j0 + per < rows ? j0 + per : rows;
   const double* Wg = Wb + (i64)gp * wb_stride_q;
-  const i64 xl = (idx_dev ? *idx_dev : idx_host) - cand0;
+  const i64 xl = (idx_dev ? __ldcg(idx_dev) : idx_host) - cand0;  // (L2 reads: see above)
   const bool have = xl >= 0 && xl < n_cand;
   double sq = 0.0;
   for (i64 j = j0 + threadIdx.x; j < j1; j += 256) {
-    const double c = pcol ? pcol[(i64)gp * pcol_stride + j] : (have ? Wg[j * ldw + xl] : 0.0);
+    const double c = pcol ? __ldcg(pcol + (i64)gp * pcol_stride + j) : (have ? __ldcg(Wg + j * ldw + xl) : 0.0);
     const double sc = fz_sign(j, m_pad) * c;
     csm[j - j0] = sc;
     sq += sc * c;
