@@ -142,6 +142,9 @@ class DeviceGP:
         self._ws_views = {}  # name -> (tensor, shape, dtype, view) of the last request
         self._cond = None  # incremental conditioning state (score_itl_directed)
         self._ctx = None   # tal_step_ctx of the fused step (built on demand)
+        self._ctx_st = None
+        self._gen = 0      # bumped whenever a buffer the context points to may have been replaced
+        self._ctx_gen = -1
         self.fused = os.environ.get("TAL_FUSED", "1") != "0"  # False: the kernel-by-kernel Python sequence
         self.cond_chunks = 0  # tal_cond_update: 0 = choose, 1 = single pass, > 1 = row-parallel
         # incremental conditioning: "append" (read-only pass + two appended rows per observation,
@@ -169,11 +172,16 @@ class DeviceGP:
         """Number of observations whose covariance updates are applied in one pass (1 = a pass per
         observation, like the reference)."""
         self.flush()
+        self._gen += 1
         self.update_block = max(1, min(_abi.TAL_MAX_PENDING, int(b)))
         if self.update_block > 1:
             self._alloc_pending()
 
     def _alloc_pending(self) -> None:
+        self._gen = getattr(self, "_gen", 0) + 1
+        self._alloc_pending_impl()
+
+    def _alloc_pending_impl(self) -> None:
         """Pending (k, w) slots (the pass is compiled for 2, 4, 8 or 16 of them; slots beyond the
         number in use are not read)."""
         slots = 2
@@ -202,6 +210,7 @@ class DeviceGP:
         conditioning column then live inside this rank's mailbox, where the
         owner of the row stores them (csrc/peer.cu).  Collective."""
         self._sel_discard()
+        self._gen += 1
         self._ctx = None  # (its cached mailbox pointers are about to be freed)
         self._peer = self.comm.attach(self.q, self.ld, self.dtype, int(m_pad), self.device)
         self.kbuf = self._peer.kbuf
@@ -242,6 +251,14 @@ class DeviceGP:
 
     def _ctx_get(self) -> "_abi.StepCtx":
         st = self._cond
+        c = self._ctx
+        if c is not None and self._ctx_gen == self._gen and self._ctx_st is st:
+            # nothing the context points to has been replaced since it was built (every site that (re)allocates one
+            # of those buffers bumps `_gen`): skip the pointer-by-pointer key
+            c.pending = self._pending
+            c.rows = st["rows"] if st is not None else 0
+            c.cond_valid = int(st is not None and st["valid"])
+            return c
         F = self._scratch("ctx_F", (max(self.n_cand, 1),))
         key = (None if st is None else (st["V"].data_ptr(), st["cap"], st["cs"].data_ptr(), st["fz"].data_ptr()),
                None if self._peer is None else (self._peer.kbuf.data_ptr(), self.comm._table.data_ptr()),
@@ -293,6 +310,7 @@ class DeviceGP:
                 c.pcol_peer, c.pcol_stride = pv.pcol.data_ptr(), pv.pcol.shape[1]
                 c.combined = self._combined.data_ptr()
             self._ctx, self._ctx_key = c, key
+        self._ctx_gen, self._ctx_st = self._gen, st
         c.pending = self._pending
         c.rows = st["rows"] if st is not None else 0
         c.cond_valid = int(st is not None and st["valid"])
@@ -965,6 +983,7 @@ class DeviceGP:
                     st["chunk"] = torch.empty((int(self.lib.tal_cond_chunk_scratch_bytes(ncols)) // 8,), **f64)
             st.update(key=roi_key, m_pad=m_pad, ncols=ncols, cap=cap, rows=m_pad, append=append, valid=False)
             self._cond = st
+            self._gen += 1
             if self._peer is not None and self._peer.m_pad < cap:
                 self._peer_attach(cap)
         if not incremental and st is not None:
@@ -1100,6 +1119,7 @@ class DeviceGP:
 
     def drop_conditioning(self) -> None:
         self._sel_discard()
+        self._gen += 1
         self._cond = None
         self._ctx = None  # (its cached pointers into the conditioning buffers are gone)
 
