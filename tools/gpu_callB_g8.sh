@@ -14,12 +14,3 @@ try:
 except Exception as e:
     print("parse", e); print(open("gpurun_out/r02b_scale_g8.err").read()[-1500:])
 PY
-TAL_BREAKDOWN=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 8 --steps 32 --warmup 3 --no-subrecords > gpurun_out/r02b_breakdown_g8.json 2> gpurun_out/r02b_breakdown_g8.err
-python - <<'PY'
-import json
-try:
-    d=json.loads(open("gpurun_out/r02b_breakdown_g8.json").read().strip().splitlines()[-1])
-    print("breakdown", 8, round(d["value"],1), round(d["ms_per_step"],4), d.get("breakdown_us"))
-except Exception as e:
-    print("parse", e); print(open("gpurun_out/r02b_breakdown_g8.err").read()[-1500:])
-PY
