@@ -1,5 +1,6 @@
 # round 2, final 8-GPU run: default bench line with the c4 / c5 (500 steps) sub-records, per-phase breakdown
 mkdir -p gpurun_out
+TAL_EXCHANGE=peer timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 tools/mp_parity.py c5 40 2>&1 | grep -v "^\*\*\*\|OMP_NUM\|^$\|^W[0-9]" | grep -E "mp parity|Error|Mismatch|Max " | tee gpurun_out/r02b_mp_parity_g8.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 32 --warmup 3 > gpurun_out/r02b_scale_g8.json 2> gpurun_out/r02b_scale_g8.err
 echo "bench g8 rc=$?"
 python - <<'PY'
