@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(256) fused_observe_kernel(FusedObs a) {
     wx_p[threadIdx.x] = Wp[(i64)threadIdx.x * a.pend_stride + idx];
   }
   T kx_raw = T(0);
-  if (threadIdx.x == 0) kx_raw = a.mailbox ? kbuf[idx] : cov[idx * ld + idx];  // (the diagonal is always kept)
+  // the stored diagonal element: local matrix, or -- sharded -- the copy its owner pushed next to the row (NOT
+  // kbuf[idx]: the block that owns element idx rewrites it in place below, a late block would correct it twice)
+  if (threadIdx.x == 0) kx_raw = a.mailbox ? T(hdr(a.mailbox)->kdiag[gp]) : cov[idx * ld + idx];
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.pending; ++i) kx_raw = sub_prod_m<FMA>(kx_raw, kx_p[i], wx_p[i]);

@@ -152,6 +152,11 @@ peer_push_row_kernel(void* const* __restrict__ boxes, int G, int rank, ShardBoun
     }
     char* box = reinterpret_cast<char*>(boxes[g]);
     if (mine) *reinterpret_cast<V16*>(reinterpret_cast<T*>(box + kbuf_off) + (i64)gp * ld + base) = v;
+    if (mine && own && idx >= base && idx < base + VN) {  // the thread that carries the diagonal element
+      T e[VN];
+      memcpy(e, &v, sizeof(v));
+      hdr(boxes[g])->kdiag[gp] = (double)e[idx - base];
+    }
     if (col_mine)
       reinterpret_cast<double*>(box + pcol_off)[(i64)gp * pcol_stride + t] =
           own_col ? V[gp * v_stride_q + t * ldv + (idx - cand0)] : 0.0;

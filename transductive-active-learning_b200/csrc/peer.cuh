@@ -24,6 +24,11 @@ struct alignas(256) PeerHeader {
   unsigned long long ready[kPeerMax];    // ready[g] = s: rank g may receive row exchange s
   unsigned long long row_seq[kPeerMax];  // row_seq[g] = s: rank g's piece of exchange s has landed here
   PeerSlot slot[2][kPeerMax];
+  // the diagonal element cov_i[x*][x*] of the row being exchanged, as stored (no pending update applied), one per
+  // GP: written by the owner of row x* together with its piece.  fused_observe corrects the row IN PLACE in kbuf,
+  // so a block that starts late must not take the diagonal from kbuf[x*] (its owner block may already have
+  // corrected it: the correction would be applied twice, and that block's weights w = k / s would be off)
+  double kdiag[TAL_MAX_Q];
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
