@@ -276,8 +276,8 @@ class DeviceGP:
             # where creating a stream while another shard's kernel spins on this one stalls until its time-out
             # (the hazard of tests/conftest.py; between processes on separate GPUs nothing is shared)
             # OPT-IN (TAL_OVERLAP=1): measured +3 % at 4 GPUs, but one full-size parity run at 4 ranks failed with it
-            # (scores of one column tile off by 2e-5 at step 15) before the protocol words were read through L2;
-            # off until that case has been re-run green
+            # (scores of one column tile off by 2e-5 at step 15) -- the signature of the kdiag race fixed since
+            # (csrc/peer.cuh); off until that case has been re-run green with the fix
             c.overlap = int(os.environ.get("TAL_OVERLAP", "0") == "1"
                             and not getattr(self.comm, "single_context", False))
             c.cov, c.cov_stride_q, c.ld, c.row0, c.n_loc = self._cov.data_ptr(), self.cov_stride_q, self.ld, self.row0, self.n_loc
